@@ -1,0 +1,170 @@
+"""oracle/ref_harness.py -- TEST INFRASTRUCTURE ONLY; runs ONLY in the build container.
+
+Imports the UNMODIFIED reference Python files from /root/reference (read-only) under a set of
+import/runtime shims so that `Network.forward(blobs, 'TEST', killing_inds)` and the operator
+modules execute on the CPU with torch 2.x.  Used by oracle/make_golden.py to produce the committed
+fixtures under tests/golden/ that pin oracle/port.py.  Nothing on the GPU box imports this file
+(/root/reference does not exist there).
+
+Shims:
+  * stub modules for deps absent from the image (easydict, ipdb, h5py, plyfile, matplotlib, skimage,
+    torchnet, tensorflow, reprint, imageio) and for the two torch-0.4 FFI packages;
+  * Tensor.cuda / Module.cuda / torch.cuda.* -> no-ops (routes nms -> numpy cpu_nms and RoI pooling
+    -> the reference's CPU C kernel, compiled unmodified into oracle/_ref/libref_roi_cpu.so);
+  * int64 `/` -> floor division (torch-0.4 LongTensor semantics, projection.py:68,70,80,82);
+  * legacy instance-style autograd.Function made callable (roi_pool.py:9-49);
+  * yaml.load default Loader; cwd = reference root (anchor tables are opened by relative path).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get("SIS3D_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class _EasyDict(dict):
+    def __init__(self, d=None, **kw):
+        super().__init__()
+        for k, v in dict(d or {}, **kw).items():
+            self[k] = v
+
+    def __setitem__(self, k, v):
+        if isinstance(v, dict) and not isinstance(v, _EasyDict):
+            v = _EasyDict(v)
+        super().__setitem__(k, v)
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    __setattr__ = __setitem__
+
+
+class _THFloat(ctypes.Structure):
+    _fields_ = [("data", ctypes.POINTER(ctypes.c_float)), ("size", ctypes.c_long * 8)]
+
+
+def _th(t):
+    s = _THFloat()
+    s.data = ctypes.cast(t.data_ptr(), ctypes.POINTER(ctypes.c_float))
+    for i, v in enumerate(t.shape):
+        s.size[i] = v
+    return s
+
+
+_installed = False
+
+
+def install():
+    """Install all shims and put the reference root on sys.path.  Idempotent."""
+    global _installed
+    if _installed:
+        return
+    if not os.path.isdir(os.path.join(REF, "lib")):
+        raise RuntimeError(f"reference tree not found at {REF}")
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    stub("easydict", EasyDict=_EasyDict)
+    stub("ipdb", set_trace=lambda *a, **k: None)
+    for name in ("h5py", "plyfile", "torchnet", "tensorflow", "reprint", "imageio", "tqdm"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                stub(name, PlyData=object, PlyElement=object, output=object, tqdm=lambda x, **k: x)
+    mpl = stub("matplotlib", use=lambda *a, **k: None)
+    mpl.pyplot = stub("matplotlib.pyplot")
+    sk = stub("skimage")
+    sk.transform = stub("skimage.transform")
+
+    # FFI packages ------------------------------------------------------------------------------
+    ref_roi = ctypes.CDLL(os.path.join(_HERE, "_ref", "libref_roi_cpu.so"))
+
+    def roi_pooling_forward(pw, ph, pl, scale, features, rois, output):
+        f, r, o = features.contiguous(), rois.contiguous().float(), output
+        return ref_roi.roi_pooling_forward(int(pw), int(ph), int(pl), ctypes.c_float(scale),
+                                           ctypes.byref(_th(f)), ctypes.byref(_th(r)), ctypes.byref(_th(o)))
+
+    ext_roi = stub("lib.layer_utils.roi_pooling._ext")
+    ext_roi.roi_pooling = stub("lib.layer_utils.roi_pooling._ext.roi_pooling",
+                               roi_pooling_forward=roi_pooling_forward)
+    ext_nms = stub("lib.layer_utils.nms._ext")
+    ext_nms.nms = stub("lib.layer_utils.nms._ext.nms")
+
+    # runtime patches ----------------------------------------------------------------------------
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+    torch.cuda.synchronize = lambda *a, **k: None
+    torch.cuda.empty_cache = lambda *a, **k: None
+    _truediv = torch.Tensor.__truediv__
+
+    def _div(self, other):
+        if not self.is_floating_point() and isinstance(other, (int, np.integer)):
+            return torch.div(self, other, rounding_mode="floor")
+        if not self.is_floating_point() and isinstance(other, torch.Tensor) and not other.is_floating_point():
+            return torch.div(self, other, rounding_mode="floor")
+        return _truediv(self, other)
+
+    torch.Tensor.__truediv__ = _div
+    import yaml
+    _load = yaml.load
+    yaml.load = lambda stream, Loader=None: _load(stream, Loader=Loader or yaml.SafeLoader)
+
+    sys.path.insert(0, REF)
+    os.chdir(REF)
+    import lib.nets.backbones  # noqa: F401  (must precede lib.nets.network: circular import)
+    import lib.layer_utils.roi_pooling.roi_pool as rp
+
+    _Fn = rp.RoIPoolFunction
+
+    class _CallableRoIPool:
+        """Instance-style wrapper executing the reference's own forward body."""
+
+        def __init__(self, pw, ph, pl, scale):
+            self.pooled_height, self.pooled_width, self.pooled_length = int(ph), int(pw), int(pl)
+            self.spatial_scale = float(scale)
+            self.argmax = self.rois = self.feature_size = None
+
+        def __call__(self, features, rois):
+            return _Fn.forward(self, features, rois)
+
+    rp.RoIPoolFunction = _CallableRoIPool
+    import lib.nets.network as net_mod
+    net_mod.RoIPoolFunction = _CallableRoIPool
+    _installed = True
+
+
+def load_cfg(yml_rel, **over):
+    """cfg_from_file + NUM_CLASSES as derived by main.py:44-50."""
+    install()
+    from lib.utils.config import cfg, cfg_from_file
+    cfg_from_file(os.path.join(REF, "experiments", "cfgs", yml_rel))
+    cfg.NUM_CLASSES = 26 if 'SUNCG' in yml_rel else 19  # = #labels with weight>0 in cfg.LABEL_MAP (main.py:44-50)
+    for k, v in over.items():
+        cfg[k] = v
+    return cfg
+
+
+def build_net(cfg, weights):
+    """getattr(backbones, cfg.NET)() + init_modules + load_state_dict (trainval.py:88-91)."""
+    from lib.nets import backbones
+    net = getattr(backbones, cfg.NET)()
+    net.init_modules()
+    sd = {k: torch.from_numpy(np.array(v)) for k, v in weights.items()}
+    missing = net.load_state_dict(sd, strict=True)
+    net.eval()
+    return net

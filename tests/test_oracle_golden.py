@@ -1,0 +1,89 @@
+"""Pins oracle/port.py against fixtures produced by the UNMODIFIED reference
+(oracle/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+import sis3d_synth as synth
+from conftest import load_golden
+
+CASES = {
+    "cfg1_32": dict(cfgname="scannet", dims=(32, 32, 32), n_img=0, seed=101, use_images=False, use_mask=False),
+    "odd_45x27x41": dict(cfgname="scannet", dims=(45, 27, 41), n_img=3, seed=202, use_images=True, use_mask=True),
+    "cfg2_96x48x96": dict(cfgname="scannet", dims=(96, 48, 96), n_img=5, seed=303, use_images=True, use_mask=True),
+    "suncg_40x24x40": dict(cfgname="suncg", dims=(40, 24, 40), n_img=3, seed=404, use_images=True, use_mask=True),
+}
+
+
+def build_case(port, c):
+    cfg = port.make_cfg(c["cfgname"], USE_IMAGES=c["use_images"], USE_MASK=c["use_mask"])
+    w = synth.make_weights(seed=0, net=cfg.NET, use_images=c["use_images"], num_classes=cfg.NUM_CLASSES,
+                           a1=cfg.NUM_ANCHORS_LEVEL1, a2=cfg.NUM_ANCHORS_LEVEL2, use_mask=c["use_mask"])
+    data, boxes = synth.make_scene(c["seed"], c["dims"])
+    views = None
+    if c["use_images"]:
+        views = synth.make_views(c["seed"], c["dims"], c["n_img"], boxes,
+                                 intrinsic=np.array(cfg.INTRINSIC, dtype=np.float32))
+    return cfg, w, data, views
+
+
+def sub(t, step):
+    return np.asarray(t, dtype=np.float32).reshape(-1)[::step]
+
+
+@pytest.mark.parametrize("tag", list(CASES))
+def test_port_matches_reference_forward(oracle, tag):
+    c = CASES[tag]
+    if tag == "cfg2_96x48x96":
+        torch.set_num_threads(max(1, torch.get_num_threads()))
+    g = load_golden(f"forward_{tag}.npz")
+    cfg, w, data, views = build_case(oracle, c)
+    out = oracle.forward(cfg, w, data, views)
+    if c["use_images"]:
+        assert list(g["killing_inds"]) == out["killing_inds"]
+        for i in range(c["n_img"]):
+            m = oracle.compute_projection(cfg, views["depths"][i], views["poses"][i], views["world2grid"], c["dims"])
+            assert np.array_equal(m[0], g[f"proj3d_{i}"]), f"view {i} lin3d"
+            assert np.array_equal(m[1], g[f"proj2d_{i}"]), f"view {i} lin2d"
+        assert np.array_equal(sub(out["imageft"], 97), g["imageft_sub"])  # exact: pure copy/max
+    for lvl in (1, 2):
+        np.testing.assert_allclose(sub(out[f"rpn_prob_level{lvl}"], 5), g[f"rpn_prob_sub_l{lvl}"], atol=2e-6)
+        np.testing.assert_allclose(sub(out[f"rpn_deltas_level{lvl}"], 11), g[f"rpn_bbox_sub_l{lvl}"], atol=2e-5)
+    assert out["rois"].shape == g["rois"].shape
+    np.testing.assert_allclose(out["rois"].numpy(), g["rois"], atol=1e-3)
+    np.testing.assert_allclose(out["roi_scores"].numpy().reshape(-1), g["roi_scores"].reshape(-1), atol=2e-6)
+    assert np.array_equal(out["level_inds"].numpy(), g["level_inds"])
+    np.testing.assert_allclose(out["cls_prob"].numpy(), g["cls_prob"], atol=1e-5)
+    assert np.array_equal(out["cls_pred"].numpy(), g["cls_pred"])
+    np.testing.assert_allclose(out["bbox_pred"].numpy(), g["bbox_pred"], atol=1e-5)
+    if c["use_mask"]:
+        np.testing.assert_allclose(out["pred_box"], g["pred_box"], atol=1e-3)
+        assert np.array_equal(out["mask_keep"], g["mask_keep"])
+        kept = np.nonzero(out["mask_keep"])[0]
+        for j, i in enumerate(kept):
+            m = out["mask_pred"][j][0].numpy()
+            np.testing.assert_allclose(m[int(g["cls_pred"][i])], g[f"mask_{j}_cls"], atol=1e-5)
+            np.testing.assert_allclose(m.reshape(-1)[::13], g[f"mask_{j}_allcls_sub"], atol=1e-5)
+
+
+def test_port_operators(oracle):
+    g = load_golden("operators.npz")
+    for seed in range(6):
+        s, n, thr = g[f"nms_cfg_{seed}"]
+        b = synth.make_nms_boxes(int(s), int(n))
+        keep = oracle.nms3d(b, float(thr), fma_mode=0)
+        assert np.array_equal(keep, g[f"nms_keep_{seed}"]), f"nms case {seed}"
+    rng = np.random.default_rng(11)
+    feat = rng.standard_normal((1, 16, 24, 12, 24)).astype(np.float32)
+    out, arg = oracle.roi_pool3d(feat, g["roi_rois"], (4, 4, 4), 0.25)
+    assert np.array_equal(out, g["roi_out"])
+    # argmax consistency: value at argmax equals the pooled value (or bin empty -> -1 / 0)
+    flat = feat.reshape(-1)
+    ok = np.where(arg >= 0, flat[np.maximum(arg, 0)], 0.0)
+    assert np.array_equal(ok, out)
+    a1 = oracle.generate_anchors([5, 3, 4], oracle.read_anchor_table("scannet14_3.txt"))
+    a2 = oracle.generate_anchors([2, 3, 2], oracle.read_anchor_table("scannet14_11.txt"))
+    assert np.array_equal(a1, g["anchors_l1_5x3x4"]) and np.array_equal(a2, g["anchors_l2_2x3x2"])
+    pb = oracle.bbox_transform_inv(a1, g["decode_deltas"])
+    assert np.array_equal(pb.numpy(), g["decode_boxes"])
+    assert np.array_equal(oracle.clip_boxes(pb, [20, 12, 16]).numpy(), g["decode_clipped"])
