@@ -1,0 +1,270 @@
+// conv_simt.cu -- fp32 implicit-GEMM 3D convolution on CUDA cores + MaxPool3d(3,1,1) + layout helpers.
+//
+// Role in the design (DESIGN.md "kernels"): exact-fp32 path for every conv call site of
+// lib/nets/backbones.py / lib/nets/network.py.  The 3x3x3 / wide-channel layers are served by the
+// tcgen05 kernel (conv_tc.cu); this kernel keeps the narrow layers (C_in = 2, tiny C_out heads) and
+// is the fp32 parity reference for the tensor-core path.
+//
+// GEMM view: M = output voxels of all regions (tiles of 64), N = C_out, K = ks^3 * C_in with
+// k = tap*C_in + c.  A is gathered on the fly from the VC (or strided NCDHW) input with zero fill
+// outside the region (== PyTorch zero padding of the *crop*, lib/nets/network.py:303-311); B is the
+// pre-packed weight [K][ldw].
+#include "common.cuh"
+
+namespace sis3d {
+
+constexpr int BM = SIS3D_CONV_TILE_M;  // 64
+constexpr int BK = 16;
+constexpr int kConvThreads = 256;
+constexpr int AS_LD = BM + 4;
+
+struct ConvArgs {
+    const float *in, *w, *bias, *res;
+    float *out;
+    const sis3d_region *regions;
+    int n_regions, cin, cout, ldw, ks, stride, pad, act, K;
+    int out_ld, out_coff, res_ld, res_coff;
+    int64_t in_sc;
+    int fast;  // in_sc == 1 && cin % 16 == 0
+};
+
+template <int BN, int TM>
+__global__ void __launch_bounds__(kConvThreads) conv3d_igemm_f32(const ConvArgs a) {
+    constexpr int TN = 4;
+    constexpr int NTX = BN / TN;  // threads along N
+    __shared__ __align__(16) float As[BK][AS_LD];
+    __shared__ __align__(16) float Bs[BK][BN];
+    __shared__ int s_region;
+
+    const int t = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int n0 = blockIdx.y * BN;
+    if (t == 0) {
+        int lo = 0, hi = a.n_regions - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (a.regions[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+        }
+        s_region = lo;
+    }
+    __syncthreads();
+    const sis3d_region R = a.regions[s_region];
+    const int oyz = R.out_dim[1] * R.out_dim[2];
+    const int m_total = R.out_dim[0] * oyz;
+    const int m_base = (tile - R.tile_begin) * BM;
+
+    // ---- A loader role: row lr, 4 consecutive k at lq*4
+    const int lr = t >> 2, lq = t & 3;
+    const int lm = m_base + lr;
+    const bool lvalid = lm < m_total;
+    int lx = 0, ly = 0, lz = 0;
+    if (lvalid) {
+        lx = lm / oyz;
+        int rem = lm - lx * oyz;
+        ly = rem / R.out_dim[2];
+        lz = rem - ly * R.out_dim[2];
+    }
+    const int bx = lx * a.stride - a.pad, by = ly * a.stride - a.pad, bz = lz * a.stride - a.pad;
+    const float *in_base = a.in + R.in_off;
+    // ---- B loader role
+    const int bk = t / (BN / 4), bc = (t % (BN / 4)) * 4;
+    const bool b_thread = t < BK * (BN / 4);
+
+    const int tx = t % NTX, ty = t / NTX;
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    const int ks2 = a.ks * a.ks;
+    for (int k0 = 0; k0 < a.K; k0 += BK) {
+        // ---------------- gather A
+        float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.fast) {
+            const int tap = k0 / a.cin, c0 = k0 - tap * a.cin + lq * 4;
+            const int kx = tap / ks2, kr = tap - kx * ks2, ky = kr / a.ks, kz = kr - ky * a.ks;
+            const int ix = bx + kx, iy = by + ky, iz = bz + kz;
+            if (lvalid && (unsigned)ix < (unsigned)R.in_dim[0] && (unsigned)iy < (unsigned)R.in_dim[1] &&
+                (unsigned)iz < (unsigned)R.in_dim[2]) {
+                const float *p = in_base + ix * R.in_stride[0] + iy * R.in_stride[1] + iz * R.in_stride[2] + c0;
+                av = __ldg(reinterpret_cast<const float4 *>(p));
+            }
+        } else {
+            float tmp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = k0 + lq * 4 + i;
+                if (lvalid && k < a.K) {
+                    const int tap = k / a.cin, c = k - tap * a.cin;
+                    const int kx = tap / ks2, kr = tap - kx * ks2, ky = kr / a.ks, kz = kr - ky * a.ks;
+                    const int ix = bx + kx, iy = by + ky, iz = bz + kz;
+                    if ((unsigned)ix < (unsigned)R.in_dim[0] && (unsigned)iy < (unsigned)R.in_dim[1] &&
+                        (unsigned)iz < (unsigned)R.in_dim[2])
+                        tmp[i] = __ldg(in_base + ix * R.in_stride[0] + iy * R.in_stride[1] +
+                                       iz * R.in_stride[2] + c * a.in_sc);
+                }
+            }
+            av = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
+        }
+        // ---------------- load B
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b_thread) {
+            const int k = k0 + bk, n = n0 + bc;
+            if (k < a.K && n < a.ldw) bv = __ldg(reinterpret_cast<const float4 *>(a.w + (int64_t)k * a.ldw + n));
+        }
+        __syncthreads();  // previous chunk fully consumed
+        As[lq * 4 + 0][lr] = av.x;
+        As[lq * 4 + 1][lr] = av.y;
+        As[lq * 4 + 2][lr] = av.z;
+        As[lq * 4 + 3][lr] = av.w;
+        if (b_thread) *reinterpret_cast<float4 *>(&Bs[bk][bc]) = bv;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float ar[TM];
+            if constexpr (TM == 4) {
+                const float4 v = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+                ar[0] = v.x; ar[1] = v.y; ar[2] = v.z; ar[3] = v.w;
+            } else {
+                const float2 v = *reinterpret_cast<const float2 *>(&As[k][ty * 2]);
+                ar[0] = v.x; ar[1] = v.y;
+            }
+            const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+#pragma unroll
+            for (int i = 0; i < TM; ++i) {
+                acc[i][0] = fmaf(ar[i], b.x, acc[i][0]);
+                acc[i][1] = fmaf(ar[i], b.y, acc[i][1]);
+                acc[i][2] = fmaf(ar[i], b.z, acc[i][2]);
+                acc[i][3] = fmaf(ar[i], b.w, acc[i][3]);
+            }
+        }
+    }
+    // ---------------- epilogue
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int m = m_base + ty * TM + i;
+        if (m >= m_total) continue;
+        float *orow = a.out + R.out_off + (int64_t)m * a.out_ld + a.out_coff;
+        const float *rrow = a.res ? a.res + R.res_off + (int64_t)m * a.res_ld + a.res_coff : nullptr;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + tx * TN + j;
+            if (n >= a.cout) continue;
+            float v = acc[i][j];
+            if (a.bias) v += a.bias[n];
+            if (rrow) v += rrow[n];
+            if (a.act == 1) v = fmaxf(v, 0.f);
+            else if (a.act == 2) v = 1.f / (1.f + expf(-v));
+            orow[n] = v;
+        }
+    }
+}
+
+// weights [cout][cin][ks][ks][ks] -> [K = tap*cin + c][ldw], zero padded columns
+__global__ void pack_conv_weight_kernel(const float *w, int cout, int cin, int ks3, int ldw, float *out) {
+    const int64_t total = (int64_t)ks3 * cin * ldw;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i % ldw);
+        const int64_t k = i / ldw;
+        const int c = (int)(k % cin), tap = (int)(k / cin);
+        out[i] = n < cout ? w[((int64_t)n * cin + c) * ks3 + tap] : 0.f;
+    }
+}
+
+// MaxPool3d(kernel 3, stride 1, pad 1) on VC; out-of-range taps ignored (PyTorch pads with -inf).
+__global__ void maxpool3_vc_kernel(const float4 *in, float4 *out, int X, int Y, int Z, int C4, int out_ld4, int out_coff4) {
+    const int64_t total = (int64_t)X * Y * Z * C4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4);
+        int64_t v = i / C4;
+        const int z = (int)(v % Z);
+        v /= Z;
+        const int y = (int)(v % Y), x = (int)(v / Y);
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = x + dx;
+            if ((unsigned)xx >= (unsigned)X) continue;
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int yy = y + dy;
+                if ((unsigned)yy >= (unsigned)Y) continue;
+                for (int dz = -1; dz <= 1; ++dz) {
+                    const int zz = z + dz;
+                    if ((unsigned)zz >= (unsigned)Z) continue;
+                    const float4 q = __ldg(in + (((int64_t)xx * Y + yy) * Z + zz) * C4 + c);
+                    m.x = fmaxf(m.x, q.x); m.y = fmaxf(m.y, q.y); m.z = fmaxf(m.z, q.z); m.w = fmaxf(m.w, q.w);
+                }
+            }
+        }
+        out[(i / C4) * out_ld4 + out_coff4 + c] = m;
+    }
+}
+
+// VC [nvox][C] -> [C][nvox] through a 32x32 smem transpose
+__global__ void vc_to_ncdhw_kernel(const float *in, float *out, int64_t nvox, int C) {
+    __shared__ float tile[32][33];
+    const int64_t v0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t v = v0 + r;
+        const int c = c0 + threadIdx.x;
+        tile[r][threadIdx.x] = (v < nvox && c < C) ? in[v * C + c] : 0.f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int c = c0 + r;
+        const int64_t v = v0 + threadIdx.x;
+        if (v < nvox && c < C) out[(int64_t)c * nvox + v] = tile[threadIdx.x][r];
+    }
+}
+
+}  // namespace sis3d
+
+using namespace sis3d;
+
+extern "C" int sis3d_pack_conv_weight(const float *w, int cout, int cin, int ks, float *w_packed, void *stream) {
+    if (!w || !w_packed || cout <= 0 || cin <= 0 || ks <= 0) return SIS3D_EINVAL;
+    const int ldw = (cout + 3) & ~3;
+    const int64_t total = (int64_t)ks * ks * ks * cin * ldw;
+    const int blocks = (int)imin64(cdiv64(total, 256), 148 * 8);
+    pack_conv_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, cout, cin, ks * ks * ks, ldw, w_packed);
+    return finish_launch();
+}
+
+extern "C" int sis3d_conv3d(const float *in, int64_t in_chan_stride, const float *w_packed, const float *bias,
+                            const float *residual, int res_ld, int res_coff, float *out, int out_ld, int out_coff,
+                            const sis3d_region *regions, int n_regions, int n_tiles, int cin, int cout, int ks,
+                            int stride, int pad, int act, void *stream) {
+    if (!in || !w_packed || !out || !regions || n_regions <= 0 || cin <= 0 || cout <= 0) return SIS3D_EINVAL;
+    if (n_tiles <= 0) return SIS3D_OK;
+    ConvArgs a;
+    a.in = in; a.w = w_packed; a.bias = bias; a.res = residual; a.out = out; a.regions = regions;
+    a.n_regions = n_regions; a.cin = cin; a.cout = cout; a.ldw = (cout + 3) & ~3; a.ks = ks; a.stride = stride;
+    a.pad = pad; a.act = act; a.K = ks * ks * ks * cin; a.out_ld = out_ld; a.out_coff = out_coff;
+    a.res_ld = res_ld; a.res_coff = res_coff; a.in_sc = in_chan_stride;
+    a.fast = (in_chan_stride == 1 && cin % 16 == 0 && ((uintptr_t)in % 16 == 0)) ? 1 : 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cout <= 32) {
+        dim3 grid(n_tiles, cdiv(cout, 32));
+        conv3d_igemm_f32<32, 2><<<grid, kConvThreads, 0, s>>>(a);
+    } else {
+        dim3 grid(n_tiles, cdiv(cout, 64));
+        conv3d_igemm_f32<64, 4><<<grid, kConvThreads, 0, s>>>(a);
+    }
+    return finish_launch();
+}
+
+extern "C" int sis3d_maxpool3(const float *in, float *out, int out_ld, int out_coff, int X, int Y, int Z, int C, void *stream) {
+    if (!in || !out || C % 4 != 0 || out_ld % 4 != 0 || out_coff % 4 != 0 || X <= 0 || Y <= 0 || Z <= 0) return SIS3D_EINVAL;
+    const int64_t total = (int64_t)X * Y * Z * (C / 4);
+    const int blocks = (int)imin64(cdiv64(total, 256), 148 * 16);
+    maxpool3_vc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4 *)in, (float4 *)out, X, Y, Z, C / 4, out_ld / 4, out_coff / 4);
+    return finish_launch();
+}
+
+extern "C" int sis3d_vc_to_ncdhw(const float *in, float *out, int64_t nvox, int C, void *stream) {
+    if (!in || !out || nvox <= 0 || C <= 0) return SIS3D_EINVAL;
+    dim3 grid((unsigned)cdiv64(nvox, 32), cdiv(C, 32));
+    vc_to_ncdhw_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(in, out, nvox, C);
+    return finish_launch();
+}

@@ -1,0 +1,97 @@
+"""ctypes binding of libsis3d.so (C ABI declared in include/sis3d.h).
+
+PyTorch is used for device memory, streams and torch.distributed only; every kernel on the hot path
+lives in libsis3d.so.  There is NO fallback: if the library is missing the import fails loudly, and
+every wrapper raises on CPU tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libsis3d.so")
+
+
+class Sis3dError(RuntimeError):
+    pass
+
+
+if not os.path.exists(_LIB_PATH):
+    raise ImportError(f"{_LIB_PATH} not found: build it with `python __graft_entry__.py build` "
+                      "(or `make -C 3d-sis_b200/csrc`); there is no CPU/PyTorch fallback for the hot path")
+lib = C.CDLL(_LIB_PATH)
+
+
+class Region(C.Structure):
+    """struct sis3d_region (include/sis3d.h)."""
+    _fields_ = [("in_off", C.c_int64), ("out_off", C.c_int64), ("res_off", C.c_int64),
+                ("in_dim", C.c_int32 * 3), ("out_dim", C.c_int32 * 3), ("in_stride", C.c_int64 * 3),
+                ("tile_begin", C.c_int32), ("pad_", C.c_int32)]
+
+
+class RpnLevel(C.Structure):
+    """struct sis3d_rpn_level (include/sis3d.h)."""
+    _fields_ = [("cls", C.c_void_p), ("deltas", C.c_void_p), ("anchor_sizes", C.c_void_p),
+                ("grid", C.c_int32 * 3), ("num_anchors", C.c_int32), ("cls_mode", C.c_int32), ("pad_", C.c_int32)]
+
+
+REGION_BYTES = C.sizeof(Region)
+TILE_M = 64
+
+# every exported symbol of include/sis3d.h (checked by tests/test_abi.py)
+SYMBOLS = ["sis3d_strerror", "sis3d_version", "sis3d_launch_count", "sis3d_nms_workspace_bytes", "sis3d_nms",
+           "sis3d_roi_pool_fwd", "sis3d_roi_pool_levels", "sis3d_project_map", "sis3d_project_compact",
+           "sis3d_project_compact_workspace_bytes", "sis3d_backproject_pairs", "sis3d_project_scatter_lists",
+           "sis3d_backproject_max", "sis3d_pack_conv_weight", "sis3d_conv3d", "sis3d_maxpool3",
+           "sis3d_vc_to_ncdhw", "sis3d_rpn_workspace_bytes", "sis3d_rpn_proposals", "sis3d_detect_decode"]
+
+lib.sis3d_strerror.restype = C.c_char_p
+lib.sis3d_launch_count.restype = C.c_int64
+lib.sis3d_nms_workspace_bytes.restype = C.c_size_t
+lib.sis3d_rpn_workspace_bytes.restype = C.c_size_t
+lib.sis3d_project_compact_workspace_bytes.restype = C.c_size_t
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        raise Sis3dError(f"libsis3d {what} failed: {lib.sis3d_strerror(rc).decode()} (code {rc})")
+
+
+def ptr(t):
+    """Device pointer of a CUDA tensor (or None)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise Sis3dError("libsis3d operates on CUDA tensors only (no CPU fallback)")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count() -> int:
+    return int(lib.sis3d_launch_count())
+
+
+def f32(x):
+    return C.c_float(float(x))
+
+
+def make_regions(entries, device):
+    """entries: list of dict(in_off,out_off,res_off,in_dim,out_dim,in_stride) -> (device uint8 tensor, n_tiles)."""
+    arr = (Region * len(entries))()
+    tiles = 0
+    for i, e in enumerate(entries):
+        r = arr[i]
+        r.in_off, r.out_off, r.res_off = int(e["in_off"]), int(e["out_off"]), int(e.get("res_off", 0))
+        for k in range(3):
+            r.in_dim[k], r.out_dim[k], r.in_stride[k] = int(e["in_dim"][k]), int(e["out_dim"][k]), int(e["in_stride"][k])
+        r.tile_begin = tiles
+        m = int(e["out_dim"][0]) * int(e["out_dim"][1]) * int(e["out_dim"][2])
+        tiles += (m + TILE_M - 1) // TILE_M
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return host.to(device), tiles

@@ -1,0 +1,416 @@
+"""`Network`: the TEST-mode forward of 3D-SIS on libsis3d kernels.
+
+Public surface kept from the reference (lib/nets/network.py): `init_modules()`, `load_state_dict()`
+with the reference's parameter names/shapes, `forward(blobs, 'TEST', killing_inds)`, the
+`_predictions` dict (`rois, roi_scores, level_inds, cls_score, cls_pred, cls_prob, bbox_pred,
+mask_pred`), `_scene_info`, and `mask_backbone(scene_crop, imageft)`.
+
+Everything between the input blobs and `_predictions` runs as hand-written CUDA (csrc/*.cu) on VC
+(channels-last) activations; nn.Module is used only as the parameter container so checkpoints of the
+reference load unchanged.  Training mode is out of scope (inference-only hot path).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+from torch import nn
+
+from lib import _sis3d as S
+from lib.layer_utils import projection as proj
+from lib.layer_utils.generate_anchors import read_anchor_sizes
+from lib.layer_utils.proposal_layer import rpn_proposals
+from lib.utils.config import cfg
+
+
+class Act:
+    """A voxel activation: tensor + spatial dims + channels; layout 'vc' ([X,Y,Z,C]) or 'ncdhw'."""
+    __slots__ = ("t", "dims", "C", "layout", "ld", "coff")
+
+    def __init__(self, t, dims, Cn, layout="vc", ld=None, coff=0):
+        self.t, self.dims, self.C, self.layout = t, tuple(int(d) for d in dims), int(Cn), layout
+        self.ld, self.coff = int(ld if ld is not None else Cn), int(coff)
+
+    @property
+    def nvox(self):
+        return self.dims[0] * self.dims[1] * self.dims[2]
+
+
+def _declare(root, dotted, shape, fan_in):
+    """Register parameter `dotted` (e.g. 'geometry1.2.conv1.weight') on nested container modules,
+    default-initialised like torch's Conv/Linear (U(-1/sqrt(fan_in), 1/sqrt(fan_in)))."""
+    parts = dotted.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if p not in mod._modules:
+            mod.add_module(p, nn.Module())
+        mod = mod._modules[p]
+    bound = 1.0 / math.sqrt(fan_in)
+    mod.register_parameter(parts[-1], nn.Parameter(torch.empty(shape).uniform_(-bound, bound), requires_grad=False))
+
+
+class Network(nn.Module):
+    # layer programs of the concrete backbones are provided by subclasses (lib/nets/backbones.py)
+    SPEC = None
+
+    def __init__(self):
+        super().__init__()
+        self._predictions = {}
+        self._feat_stride = [4, 4, 4]
+        self._packed = {}
+        self._packed_version = None
+        self._region_cache = {}
+        self._const_cache = {}
+        self._keep_debug = False
+
+    # ------------------------------------------------------------------ parameters
+    def _declare_conv(self, name, cout, cin, ks, bias):
+        _declare(self, name + ".weight", (cout, cin, ks, ks, ks), cin * ks ** 3)
+        if bias:
+            _declare(self, name + ".bias", (cout,), cin * ks ** 3)
+
+    def _declare_bottleneck(self, name, inpl, planes):
+        self._declare_conv(name + ".conv1", planes, inpl, 1, True)
+        self._declare_conv(name + ".conv2", planes, planes, 3, True)
+        self._declare_conv(name + ".conv3", inpl, planes, 1, True)
+
+    def _declare_linear(self, name, cout, cin):
+        _declare(self, name + ".weight", (cout, cin), cin)
+        _declare(self, name + ".bias", (cout,), cin)
+
+    def _declare_stack(self, prefix, spec):
+        for op in spec:
+            if op[0] in ("k2s2", "k3"):
+                self._declare_conv(f"{prefix}.{op[1]}", op[3], op[2], 2 if op[0] == "k2s2" else 3, False)
+            elif op[0] == "bneck":
+                self._declare_bottleneck(f"{prefix}.{op[1]}", op[2], op[3])
+
+    def _init_backbone_classifier(self):
+        raise NotImplementedError
+
+    def init_modules(self):
+        """Declare every parameter of the 3D model (reference: network.py:35-64)."""
+        self._init_backbone_classifier()
+        if cfg.USE_RPN:
+            for lvl in (1, 2, 3):
+                A = cfg["NUM_ANCHORS_LEVEL%d" % lvl]
+                if A:
+                    self._declare_conv(f"rpn_net_level{lvl}", cfg.RPN_CHANNELS, 128, 3, True)
+                    self._declare_conv(f"rpn_cls_score_net_level{lvl}.0", 2 * A, cfg.RPN_CHANNELS, 1, True)
+                    self._declare_conv(f"rpn_bbox_pred_net_level{lvl}", 6 * A, cfg.RPN_CHANNELS, 1, True)
+        if cfg.USE_CLASS:
+            self._declare_linear("classifier_cls_score_net", cfg.NUM_CLASSES, 128)
+            self._declare_linear("classifier_bbox_pred_net", cfg.NUM_CLASSES * 6, 128)
+        if cfg.USE_MASK:
+            from lib.nets import backbones
+            self.mask_backbone = getattr(backbones, cfg.MASK_BACKBONE)()
+            self.mask_backbone._owner = [self]
+        if cfg.USE_IMAGES and not cfg.USE_IMAGES_GT:
+            # the 2D ENet encoder is upstream of the hot path; callers feed ENet-shaped
+            # features (USE_IMAGES_GT semantics) or attach their own torch modules here.
+            self.image_enet_fixed = self.image_enet_trainable = None
+
+    # ------------------------------------------------------------------ packed weights
+    def _version(self):
+        return tuple((n, p._version, p.data_ptr()) for n, p in self.named_parameters())
+
+    def _ensure_packed(self):
+        if not torch.cuda.is_available():
+            raise S.Sis3dError("the sm_100a hot path needs a CUDA device (no CPU fallback)")
+        if next(self.parameters()).device.type != "cuda":
+            self.cuda()
+        v = self._version()
+        if v == self._packed_version:
+            return
+        self._packed = {}
+        params = dict(self.named_parameters())
+        for name, p in params.items():
+            if not name.endswith(".weight"):
+                continue
+            base = name[:-7]
+            w = p.detach().float().contiguous()
+            if w.dim() == 2:
+                w = w.reshape(w.shape[0], w.shape[1], 1, 1, 1)
+            cout, cin, ks = w.shape[0], w.shape[1], w.shape[2]
+            ldw = (cout + 3) // 4 * 4
+            packed = torch.empty(ks ** 3 * cin, ldw, dtype=torch.float32, device=w.device)
+            S.check(S.lib.sis3d_pack_conv_weight(S.ptr(w), cout, cin, ks, S.ptr(packed), S.stream()), "pack")
+            b = params.get(base + ".bias")
+            self._packed[base] = (packed, None if b is None else b.detach().float().contiguous(), cout, cin, ks)
+        torch.cuda.current_stream().synchronize()
+        self._packed_version = v
+
+    # ------------------------------------------------------------------ primitive ops
+    def _regions_single(self, x: Act, out_dims, stride):
+        key = ("single", x.dims, x.C, x.layout, x.ld, tuple(out_dims), stride)
+        hit = self._region_cache.get(key)
+        if hit is None:
+            X, Y, Z = x.dims
+            strides = (Y * Z * x.ld, Z * x.ld, x.ld) if x.layout == "vc" else (Y * Z, Z, 1)
+            hit = S.make_regions([dict(in_off=0, out_off=0, res_off=0, in_dim=x.dims, out_dim=out_dims,
+                                       in_stride=strides)], x.t.device)
+            self._region_cache[key] = hit
+        return hit
+
+    def _conv(self, x: Act, name, stride=1, pad=None, act=0, residual: Act = None, out: Act = None,
+              regions=None, out_dims=None):
+        packed, bias, cout, cin, ks = self._packed[name]
+        if cin != x.C:
+            raise S.Sis3dError(f"{name}: expected {cin} input channels, got {x.C}")
+        if pad is None:
+            pad = 1 if ks == 3 else 0
+        if out_dims is None:
+            out_dims = tuple(d // 2 for d in x.dims) if stride == 2 else x.dims
+        if regions is None:
+            regions, n_tiles = self._regions_single(x, out_dims, stride)
+        else:
+            regions, n_tiles = regions
+        if out is None:
+            out = Act(torch.empty(*out_dims, cout, dtype=torch.float32, device=x.t.device), out_dims, cout)
+        in_sc = 1 if x.layout == "vc" else x.nvox
+        xin = x.t if x.coff == 0 else x.t.reshape(-1)[x.coff:]
+        S.check(S.lib.sis3d_conv3d(S.ptr(xin), C.c_int64(in_sc), S.ptr(packed), S.ptr(bias),
+                                   S.ptr(residual.t) if residual is not None else None,
+                                   residual.ld if residual is not None else 0,
+                                   residual.coff if residual is not None else 0,
+                                   S.ptr(out.t), out.ld, out.coff, S.ptr(regions), regions.numel() // S.REGION_BYTES,
+                                   n_tiles, cin, cout, ks, stride, pad, act, S.stream()), f"conv3d[{name}]")
+        return out
+
+    def _bottleneck(self, x: Act, name, out: Act = None):
+        """1x1 -> relu -> 3x3x3 -> relu -> 1x1 (+x) -> relu  (reference: backbones.py:28-40)."""
+        y = self._conv(x, name + ".conv1", act=1)
+        y = self._conv(y, name + ".conv2", act=1)
+        return self._conv(y, name + ".conv3", act=1, residual=x, out=out)
+
+    def _pool(self, x: Act, out: Act = None):
+        if out is None:
+            out = Act(torch.empty(*x.dims, x.C, dtype=torch.float32, device=x.t.device), x.dims, x.C)
+        if x.ld != x.C or x.coff:
+            raise S.Sis3dError("maxpool3 expects a dense VC input")
+        S.check(S.lib.sis3d_maxpool3(S.ptr(x.t), S.ptr(out.t), out.ld, out.coff, *x.dims, x.C, S.stream()), "maxpool3")
+        return out
+
+    def _run_stack(self, x: Act, prefix, spec, final_out=None):
+        """Execute a backbone stage program; the last op writes into `final_out` (a slice of the
+        concatenated level-1 tensor) when given."""
+        for i, op in enumerate(spec):
+            dst = final_out(x, op) if (final_out is not None and i == len(spec) - 1) else None
+            if op[0] == "k2s2":
+                x = self._conv(x, f"{prefix}.{op[1]}", stride=2, pad=0, act=1, out=dst)
+            elif op[0] == "k3":
+                x = self._conv(x, f"{prefix}.{op[1]}", act=1, out=dst)
+            elif op[0] == "bneck":
+                x = self._bottleneck(x, f"{prefix}.{op[1]}", out=dst)
+            elif op[0] == "pool":
+                x = self._pool(x, out=dst)
+        return x
+
+    # ------------------------------------------------------------------ stages of the forward
+    def _const(self, key, builder):
+        v = self._const_cache.get(key)
+        if v is None:
+            v = builder()
+            self._const_cache[key] = v
+        return v
+
+    def _backproject(self, blobs, killing_inds, dims, dev):
+        """Views -> VC feature volume (reference: trainval.py:797-820 + network.py:194-239)."""
+        imgs = blobs["nearest_images"]
+        feats = imgs["images"][0]
+        if not cfg.USE_IMAGES_GT:
+            if getattr(self, "image_enet_fixed", None) is None:
+                raise S.Sis3dError("USE_IMAGES_GT=False needs the 2D ENet encoder (upstream of the hot path, "
+                                   "SURVEY 8f2): attach torch modules as net.image_enet_fixed/_trainable or feed "
+                                   "ENet-shaped features with USE_IMAGES_GT=True")
+            with torch.no_grad():
+                feats = self.image_enet_trainable(self.image_enet_fixed(feats.to(dev)))
+        feats = feats.to(dev, torch.float32, non_blocking=True)
+        n = feats.shape[0]
+        w, h = int(cfg.DEPTH_SHAPE[0]), int(cfg.DEPTH_SHAPE[1])
+        if "proj_ind_3d" in blobs:
+            # reference calling convention: precomputed, stacked index lists + killing_inds
+            l3 = blobs["proj_ind_3d"][0].to(dev).contiguous()
+            l2 = blobs["proj_ind_2d"][0].to(dev).contiguous()
+            nreal = l3.shape[0]
+            pix = torch.empty(nreal, dims[0] * dims[1] * dims[2], dtype=torch.int16, device=dev)
+            S.check(S.lib.sis3d_project_scatter_lists(S.ptr(l3), S.ptr(l2), nreal, *dims, S.ptr(pix), S.stream()), "scatter")
+            kill = set(int(k) for k in (killing_inds or []))
+            pl = [(k, k) for k in range(min(n, nreal)) if k not in kill]  # zip(imageft, proj3d) + skip by position
+            if not pl:
+                raise S.Sis3dError("every view was skipped: nothing to back-project")
+            pairs = torch.tensor([v for p in pl for v in p], dtype=torch.int32).to(dev)
+            n_pairs = torch.tensor([len(pl)], dtype=torch.int32, device=dev)
+            self._proj_counts = None
+        else:
+            # fused path: depth/pose/world2grid in, no index lists ever materialised
+            vp = proj.view_params(cfg.INTRINSIC, (w, h), cfg.PROJ_DEPTH_MIN, cfg.PROJ_DEPTH_MAX, dims,
+                                  None, imgs["poses"][0], imgs["world2grid"][0]).to(dev, non_blocking=True)
+            depths = torch.as_tensor(imgs["depths"][0]).to(dev, torch.float32, non_blocking=True).contiguous()
+            intr = self._const(("intr", dev), lambda: torch.tensor(
+                [cfg.INTRINSIC[0][0], cfg.INTRINSIC[1][1], cfg.INTRINSIC[0][2], cfg.INTRINSIC[1][2]],
+                dtype=torch.float32, device=dev))
+            pix, counts = proj.project_maps(vp, depths, intr, (cfg.PROJ_DEPTH_MIN, cfg.PROJ_DEPTH_MAX, cfg.VOXEL_SIZE),
+                                            dims, w, h)
+            pairs = torch.empty(3 * n, dtype=torch.int32, device=dev)
+            n_pairs = torch.empty(1, dtype=torch.int32, device=dev)
+            S.check(S.lib.sis3d_backproject_pairs(S.ptr(counts), n, S.ptr(pairs), S.ptr(n_pairs), S.stream()), "pairs")
+            self._proj_counts = counts
+        vol = proj.backproject(feats, pix, pairs, n_pairs, dims, w, h)
+        return Act(vol, dims, feats.shape[1])
+
+    def _backbone(self, scene: Act, imageft: Act):
+        """reference: backbones.py:98-113.  Concatenation is free: both producers write their slice of
+        the level-1 tensor directly (colour channels first, then geometry)."""
+        spec = self.SPEC
+        dev = scene.t.device
+        if cfg.USE_IMAGES:
+            d4 = tuple((d // 2) // 2 for d in scene.dims)
+            level1 = Act(torch.empty(*d4, 128, dtype=torch.float32, device=dev), d4, 128)
+            self._run_stack(imageft, "color", spec["color"],
+                            final_out=lambda x, op: Act(level1.t, d4, 64, ld=128, coff=0))
+            self._run_stack(scene, "geometry1", spec["geometry1"],
+                            final_out=lambda x, op: Act(level1.t, d4, 64, ld=128, coff=64))
+        else:
+            level1 = self._run_stack(scene, "geometry1", spec["geometry1"])
+        level2 = self._run_stack(level1, "geometry2", spec["geometry2"])
+        return level1, level2
+
+    def _region_proposal(self, feats, dims):
+        """reference: network.py:537-587 + 657-683 (softmax/anchors/decode/top-N/NMS fused on device)."""
+        levels = []
+        for lvl, f in enumerate(feats, 1):
+            A = cfg["NUM_ANCHORS_LEVEL%d" % lvl]
+            if not A or f is None:
+                continue
+            h = self._conv(f, f"rpn_net_level{lvl}", act=1)
+            cls = self._conv(h, f"rpn_cls_score_net_level{lvl}.0")
+            bbox = self._conv(h, f"rpn_bbox_pred_net_level{lvl}")
+            name = cfg["ANCHORS_TYPE_LEVEL%d" % lvl]
+            sizes = self._const(("anchors", name, f.t.device), lambda: torch.tensor(
+                read_anchor_sizes(name), dtype=torch.float32, device=f.t.device).contiguous())
+            if sizes.shape[0] != A:
+                raise S.Sis3dError(f"anchor table {name} has {sizes.shape[0]} rows, cfg says {A}")
+            levels.append(dict(cls=cls.t, deltas=bbox.t, sizes=sizes, grid=f.dims, A=A, cls_mode=0))
+            if self._keep_debug:
+                self._predictions[f"rpn_cls_logits_level{lvl}"] = cls.t
+                self._predictions[f"rpn_bbox_pred_level{lvl}"] = bbox.t
+        res = rpn_proposals(levels, dims, "TEST", want_order=self._keep_debug)
+        if self._keep_debug:
+            self._predictions["rpn_order"] = res[4]
+        return res[:4]
+
+    def _classify(self, feats, rois, level_ids):
+        """RoI pooling per pyramid level + MLP + heads (reference: network.py:503-534, backbones.py:92-96,
+        network.py:589-604).  Always processes the padded post-NMS row count; rows >= num are zeros."""
+        P = int(cfg.CLASS_POOLING_SIZE)
+        R = rois.shape[0]
+        f1 = feats[0]
+        dev = rois.device
+        pool5 = torch.empty(R, f1.C * P ** 3, dtype=torch.float32, device=dev)
+        f = [x.t if x is not None else None for x in feats] + [None, None]
+        S.check(S.lib.sis3d_roi_pool_levels(S.ptr(f[0]), S.ptr(f[1]), S.ptr(f[2]), S.ptr(level_ids),
+                                            S.f32(1.0 / self._feat_stride[0]), R, *f1.dims, f1.C, P, P, P, S.ptr(rois),
+                                            S.ptr(pool5), None, S.stream()), "roi_pool_levels")
+        x = Act(pool5, (R, 1, 1), pool5.shape[1])
+        for i in (0, 2, 4):
+            x = self._conv(x, f"classifier.{i}", act=1)
+        cls_score = self._conv(x, "classifier_cls_score_net")
+        bbox_pred = self._conv(x, "classifier_bbox_pred_net")
+        if self._keep_debug:
+            self._predictions["pool5"] = pool5
+        return cls_score.t.view(R, -1), bbox_pred.t.view(R, -1)
+
+    def _mask_branch(self, scene_ncdhw, det_host, n):
+        """Ragged per-RoI mask head (reference: network.py:283-317): all kept crops go through each of
+        the six layers in ONE launch per layer via a region table."""
+        keep = [i for i in range(n) if det_host[i, 8] > 0.5]
+        if not keep:
+            return []
+        dev = scene_ncdhw.device
+        X, Y, Z = scene_ncdhw.shape[2:]
+        crops = [[int(v) for v in det_host[i, 9:15]] for i in keep]
+        sizes = [(c[3] - c[0], c[4] - c[1], c[5] - c[2]) for c in crops]
+        vox = [s[0] * s[1] * s[2] for s in sizes]
+        offs = np.concatenate([[0], np.cumsum(vox)]).astype(np.int64)
+        total = int(offs[-1])
+        mb = self.mask_backbone
+        bufs = [torch.empty(total * 64, dtype=torch.float32, device=dev) for _ in range(2)]
+        ncls = self._packed["mask_backbone.geometry.10"][2]
+        outb = torch.empty(total * ncls, dtype=torch.float32, device=dev)
+        first = S.make_regions([dict(in_off=(c[0] * Y + c[1]) * Z + c[2], out_off=int(offs[j]) * 64, in_dim=s, out_dim=s,
+                                     in_stride=(Y * Z, Z, 1)) for j, (c, s) in enumerate(zip(crops, sizes))], dev)
+        mid = S.make_regions([dict(in_off=int(offs[j]) * 64, out_off=int(offs[j]) * 64, in_dim=s, out_dim=s,
+                                   in_stride=(s[1] * s[2] * 64, s[2] * 64, 64)) for j, s in enumerate(sizes)], dev)
+        last = S.make_regions([dict(in_off=int(offs[j]) * 64, out_off=int(offs[j]) * ncls, in_dim=s, out_dim=s,
+                                    in_stride=(s[1] * s[2] * 64, s[2] * 64, 64)) for j, s in enumerate(sizes)], dev)
+        scene = Act(scene_ncdhw, (X, Y, Z), 2, layout="ncdhw")
+        x = self._conv(scene, "mask_backbone.geometry.0", act=1, regions=first, out_dims=(total, 1, 1),
+                       out=Act(bufs[0], (total, 1, 1), 64))
+        for li, idx in enumerate((2, 4, 6, 8)):
+            x = self._conv(x, f"mask_backbone.geometry.{idx}", act=1, regions=mid, out_dims=(total, 1, 1),
+                           out=Act(bufs[(li + 1) % 2], (total, 1, 1), 64))
+        y = self._conv(x, "mask_backbone.geometry.10", pad=0, act=2, regions=last, out_dims=(total, 1, 1),
+                       out=Act(outb, (total, 1, 1), ncls))
+        masks = []
+        for j, s in enumerate(sizes):
+            m = y.t[int(offs[j]) * ncls:int(offs[j + 1]) * ncls].view(s[0], s[1], s[2], ncls)
+            masks.append(m.permute(3, 0, 1, 2).unsqueeze(0))  # [1,ncls,w,h,l] view, reference layout
+        return masks
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, blobs, mode="TEST", killing_inds=None):
+        if mode != "TEST":
+            raise NotImplementedError("only the inference (TEST) forward is implemented on the B200 path")
+        self._ensure_packed()
+        dev = next(self.parameters()).device
+        data = blobs["data"]
+        if data.shape[0] != 1:
+            raise S.Sis3dError("batch size 1 only (as the reference's RoI pooling / proposal layer)")
+        self._scene_info = data.shape[2:]
+        self._id = blobs["id"][0] if "id" in blobs else None
+        self.batch_size = 1
+        self._mode = "TEST"
+        dims = tuple(int(v) for v in data.shape[2:])
+        P = self._predictions
+        with torch.no_grad():
+            scene_t = data.to(dev, torch.float32, non_blocking=True).contiguous()
+            self._scene = scene_t
+            scene = Act(scene_t, dims, 2, layout="ncdhw")
+            imageft = None
+            if cfg.USE_IMAGES:
+                imageft = self._backproject(blobs, killing_inds, dims, dev)
+                self._imageft_vc = imageft.t if self._keep_debug else None
+            level1, level2 = self._backbone(scene, imageft) if cfg.USE_BACKBONE else (None, None)
+            if self._keep_debug:
+                P["level1_vc"], P["level2_vc"] = level1.t, level2.t
+            if not cfg.USE_RPN:
+                raise NotImplementedError("USE_RPN=False (ground-truth boxes as RoIs) is a training/ablation mode")
+            rois, scores, level_ids, num = self._region_proposal((level1, level2, None), dims)
+            det = None
+            if cfg.USE_CLASS:
+                cls_score, bbox_pred = self._classify((level1, level2, None), rois, level_ids)
+                R, nc = rois.shape[0], int(cfg.NUM_CLASSES)
+                cls_prob = torch.empty(R, nc, dtype=torch.float32, device=dev)
+                cls_pred = torch.empty(R, dtype=torch.int64, device=dev)
+                det = torch.empty(R, 16, dtype=torch.float32, device=dev)
+                S.check(S.lib.sis3d_detect_decode(S.ptr(rois), S.ptr(num), R, S.ptr(cls_score), S.ptr(bbox_pred), nc,
+                                                  *dims, S.f32(cfg.CLASS_THRESH), S.ptr(cls_prob), S.ptr(cls_pred),
+                                                  S.ptr(det), S.stream()), "detect_decode")
+            # the one host round trip of the forward: RoI count + decoded detections (<= 13 KB)
+            n = int(num.item())
+            P["rois"], P["roi_scores"], P["level_inds"] = [rois[:n]], [scores[:n].view(-1, 1)], [level_ids[:n].float()]
+            if cfg.USE_CLASS:
+                P["cls_score"], P["cls_pred"], P["cls_prob"] = cls_score[:n], cls_pred[:n], cls_prob[:n]
+                P["bbox_pred"] = bbox_pred[:n]
+                P["detections"] = det[:n]
+                if cfg.USE_MASK:
+                    det_host = det[:n].cpu().numpy() if n else np.zeros((0, 16), np.float32)
+                    P["mask_pred"] = [self._mask_branch(scene_t, det_host, n)]
+                    P["detections_host"] = det_host
+        return P
+
+    def delete_intermediate_states(self):
+        self._predictions.clear()

@@ -1,0 +1,171 @@
+/*
+ * sis3d.h -- C ABI of libsis3d.so: the B200 (sm_100a) dense-voxel inference hot path of 3D-SIS.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer unless named h_*;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream, allocate
+ *     nothing and never call exit(); caller owns all memory (workspace sizes via *_workspace_bytes);
+ *   - return 0 on success, a negative SIS3D_E* code otherwise (see sis3d_strerror);
+ *   - "VC layout" = channels-last voxel tensor [X][Y][Z][C] fp32 (C contiguous); "NCDHW" = the
+ *     reference's [1][C][X][Y][Z] layout.
+ *
+ * Each entry cites the reference interface it replaces (paths relative to the reference root).
+ */
+#ifndef SIS3D_H
+#define SIS3D_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIS3D_OK 0
+#define SIS3D_EINVAL (-1)   /* bad argument (shape, alignment, null pointer) */
+#define SIS3D_ELAUNCH (-2)  /* CUDA launch / runtime error (cudaGetLastError) */
+#define SIS3D_EWORKSPACE (-3)
+#define SIS3D_EUNSUPPORTED (-4)
+
+const char *sis3d_strerror(int code);
+int sis3d_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t sis3d_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3D greedy NMS.  Replaces  int gpu_nms(THLongTensor* keep, THLongTensor* num_out, THCudaTensor*
+ * boxes, float thresh)  (lib/layer_utils/nms/src/nms_cuda.h:1, src/nms_cuda.c:10-67) and the kernel
+ * ABI  void _nms(int, float*, unsigned long long*, float)  (src/cuda/nms_kernel.h:14).
+ * boxes [n,6] fp32 sorted by descending score; keep int64[n] (device), num_out int32[1] (device).
+ * IoU arithmetic is bit-identical to the reference CUDA build (inclusive +1 extents, one FFMA).
+ * workspace: sis3d_nms_workspace_bytes(n) bytes, 8-byte aligned.
+ * ---------------------------------------------------------------------------------------------- */
+size_t sis3d_nms_workspace_bytes(int n);
+int sis3d_nms(const float *boxes, int n, float thresh, int64_t *keep, int32_t *num_out,
+              void *workspace, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3D RoI max pooling forward.  Replaces  int ROIPoolForwardLaucher(const float* bottom, float
+ * scale, int num_rois, int width, int height, int length, int channels, int pw, int ph, int pl,
+ * const float* rois, float* top, int* argmax, cudaStream_t)
+ * (lib/layer_utils/roi_pooling/src/cuda/roi_pooling_kernel.h:8-12) and roi_pooling_forward_cuda
+ * (src/roi_pooling_cuda.h:1-2).  feat_layout: 0 = NCDHW (reference), 1 = VC.
+ * rois [n,6]; top [n,C,pw,ph,pl]; argmax int32 same shape or NULL (indices in the NCDHW convention).
+ * sis3d_roi_pool_levels is the pyramid form used by the forward (lib/nets/network.py:503-534): VC
+ * features of up to three levels, level_ids int32[n] (1-based, 0 = padded row -> zeros) pick the map.
+ * ---------------------------------------------------------------------------------------------- */
+int sis3d_roi_pool_fwd(const float *feat, int feat_layout, float spatial_scale, int num_rois,
+                       int width, int height, int length, int channels, int pw, int ph, int pl,
+                       const float *rois, float *top, int32_t *argmax, void *stream);
+int sis3d_roi_pool_levels(const float *feat1, const float *feat2, const float *feat3,
+                          const int32_t *level_ids, float spatial_scale, int num_rois, int width,
+                          int height, int length, int channels, int pw, int ph, int pl,
+                          const float *rois, float *top, int32_t *argmax, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Back-projection.  Replaces ProjectionHelper.compute_projection (lib/layer_utils/projection.py:
+ * 52-121) and Projection.forward + the running max of lib/nets/network.py:220-239.
+ *
+ * views: float[n_views][40] per view = world_to_camera(16) | grid_to_world(16) | bounds_min(3) |
+ *        bounds_max(3) | pad(2)   (row-major 4x4; bounds already clamped to the volume)
+ * depth: float[n_views][img_h][img_w];   intr = {fx, fy, cx, cy}
+ * sis3d_project_map     : pix int16[n_views][Z*Y*X] = v*img_w+u of the pixel a voxel projects to or
+ *                         -1; index = z*X*Y + y*X + x (the reference's linear index); counts
+ *                         int32[n_views] = number of valid voxels per view (zeroed by the call).
+ * sis3d_project_compact : ordered compaction of one view's map into the reference's (lin3d, lin2d)
+ *                         int64 lists of length 1+Z*Y*X with element 0 = count.
+ * sis3d_backproject_max : fused gather + cross-view max into a VC volume [X][Y][Z][C]; reproduces
+ *                         the reference's pairing of feature maps with surviving index lists when
+ *                         views are dropped (pairs from sis3d_backproject_pairs), see DESIGN.md.  feats [n_views][C][h][w]
+ *                         (reference layout) are first transposed to [n_views][h*w][C] into
+ *                         `feats_t` (workspace of the same size).
+ * ---------------------------------------------------------------------------------------------- */
+int sis3d_project_map(const float *views, const float *depth, int n_views, int img_w, int img_h,
+                      const float *intr, float depth_min, float depth_max, float voxel_size,
+                      int X, int Y, int Z, int16_t *pix, int32_t *counts, void *stream);
+int sis3d_project_compact(const int16_t *pix, int X, int Y, int Z, int64_t *lin3d, int64_t *lin2d,
+                          void *workspace, size_t workspace_bytes, void *stream);
+size_t sis3d_project_compact_workspace_bytes(int X, int Y, int Z);
+/* pairs int32[3*n_views] (2*n_pairs used), n_pairs int32[1]: (feature map, index map) pairing derived
+ * on the device from counts -- no host round trip. */
+int sis3d_backproject_pairs(const int32_t *counts, int n_views, int32_t *pairs, int32_t *n_pairs, void *stream);
+/* reference-style index lists [n_lists][1+Z*Y*X] (lib/layer_utils/projection.py:110-121) -> dense maps */
+int sis3d_project_scatter_lists(const int64_t *lin3d, const int64_t *lin2d, int n_lists, int X, int Y, int Z,
+                                int16_t *pix, void *stream);
+int sis3d_backproject_max(const float *feats, float *feats_t, const int16_t *pix,
+                          const int32_t *pairs, const int32_t *n_pairs, int n_views, int C,
+                          int img_w, int img_h, int X, int Y, int Z, float *volume_vc, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3D convolution (implicit GEMM) over a table of regions.  Replaces the nn.Conv3d call sites of
+ * lib/nets/backbones.py:20-22,126-169,188-231,241-272 and lib/nets/network.py:40-52 (cuDNN in the
+ * reference).  One launch processes `n_regions` independent volumes (1 for the backbone, one per
+ * RoI crop for the mask head, lib/nets/network.py:303-317).
+ * Weights are pre-packed by sis3d_pack_conv_weight into [ks^3*cin][cout] (k = tap*cin + c,
+ * tap = (kx*ks+ky)*ks+kz).  Output is VC with row stride out_ld and channel offset out_coff (lets a
+ * producer write straight into a concatenated tensor); optional bias[cout], residual (VC, res_ld /
+ * res_coff), act: 0 none, 1 relu, 2 sigmoid.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct sis3d_region {
+    int64_t in_off;   /* element offset of the region's input voxel (0,0,0) */
+    int64_t out_off;  /* element offset of the region's output voxel (0,0,0), before out_coff */
+    int64_t res_off;
+    int32_t in_dim[3];     /* input extent (x,y,z): taps outside read as zero */
+    int32_t out_dim[3];    /* output extent */
+    int64_t in_stride[3];  /* input voxel strides in elements (x,y,z) */
+    int32_t tile_begin;    /* first M-tile of this region (exclusive prefix sum of tile counts) */
+    int32_t pad_;
+} sis3d_region;
+
+#define SIS3D_CONV_TILE_M 64
+int sis3d_pack_conv_weight(const float *w_oidhw, int cout, int cin, int ks, float *w_packed, void *stream);
+int sis3d_conv3d(const float *in, int64_t in_chan_stride, const float *w_packed, const float *bias,
+                 const float *residual, int res_ld, int res_coff, float *out, int out_ld, int out_coff,
+                 const sis3d_region *regions, int n_regions, int n_tiles, int cin, int cout, int ks,
+                 int stride, int pad, int act, void *stream);
+/* MaxPool3d(3,1,1) on a VC tensor (lib/nets/backbones.py:207,212,220); output row stride out_ld and
+ * channel offset out_coff as for the convolution. */
+int sis3d_maxpool3(const float *in, float *out, int out_ld, int out_coff, int X, int Y, int Z, int C, void *stream);
+/* VC [X][Y][Z][C] -> NCDHW [C][X][Y][Z] (to hand tensors back in the reference layout). */
+int sis3d_vc_to_ncdhw(const float *in, float *out, int64_t nvox, int C, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * RPN proposals ("rpn3d").  Replaces proposal_layer (lib/layer_utils/proposal_layer.py:11-204),
+ * the softmax of lib/nets/network.py:546, generate_anchors (lib/layer_utils/generate_anchors.py:
+ * 58-119), bbox_transform_inv / clip_boxes (lib/utils/bbox_transform.py:59-99,4-21) and the nms call
+ * (proposal_layer.py:190) in three launches with no host round trip.
+ * Per level l: cls [N_l][2*A_l] VC logits (channel = cls*A+a), deltas [N_l][6*A_l] VC,
+ * anchor_sizes float[A_l][3], grid (gx,gy,gz), N_l = gx*gy*gz.
+ * Outputs: rois [post_top_n][6], scores [post_top_n], level_ids int32[post_top_n] (1-based),
+ * num_out int32[1]; debug_order int32[pre_top_n] (flat anchor index of each pre-NMS box, or NULL).
+ * Tie rule: equal scores are ordered by ascending flat index (level, x, y, z, a).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct sis3d_rpn_level {
+    const float *cls;
+    const float *deltas;
+    const float *anchor_sizes;
+    int32_t grid[3];
+    int32_t num_anchors;
+    int32_t cls_mode; /* 0: cls = logits [N][2A]; 1: cls = foreground probability [N][A] */
+    int32_t pad_;
+} sis3d_rpn_level;
+size_t sis3d_rpn_workspace_bytes(const sis3d_rpn_level *h_levels, int n_levels, int pre_top_n);
+int sis3d_rpn_proposals(const sis3d_rpn_level *h_levels, int n_levels, int feat_stride,
+                        int scene_x, int scene_y, int scene_z, int allow_border, int pre_top_n,
+                        int post_top_n, float nms_thresh, float *rois, float *scores,
+                        int32_t *level_ids, int32_t *num_out, int32_t *debug_order,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Detection decode for the mask branch.  Replaces lib/nets/network.py:285-301 (== lib/model/
+ * trainval.py:825-858): argmax class, softmax confidence, class-specific bbox_transform_inv,
+ * clip, conf > class_thresh and round()-degenerate filter (Python-3 half-to-even).
+ * det float[n][16] = pred_box(6) | conf | cls | keep | crop lo(3) hi(3) | pad   (all as float)
+ * n is read from device num_rois (int32[1]) and clamped to max_rois.
+ * ---------------------------------------------------------------------------------------------- */
+int sis3d_detect_decode(const float *rois, const int32_t *num_rois, int max_rois,
+                        const float *cls_score, const float *bbox_pred, int num_classes,
+                        int scene_x, int scene_y, int scene_z, float class_thresh,
+                        float *cls_prob, int64_t *cls_pred, float *det, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIS3D_H */

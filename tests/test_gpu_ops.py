@@ -1,0 +1,343 @@
+"""Operator-level parity on the GPU (run with -m gpu on a B200): every call goes through the C ABI
+(libsis3d.so via ctypes) and is compared with the CPU oracle on the same seeded inputs."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import sis3d_synth as synth
+from conftest import ROOT, load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def S():
+    from lib import _sis3d
+    return _sis3d
+
+
+# ---------------------------------------------------------------- NMS
+@pytest.mark.parametrize("seed,n,thr", [(0, 400, 0.1), (1, 400, 0.35), (2, 1000, 0.5), (3, 64, 0.1), (4, 65, 0.7),
+                                        (5, 1, 0.1), (6, 2500, 0.3)])
+def test_nms_bit_exact(oracle, seed, n, thr):
+    from lib.layer_utils.nms_wrapper import nms
+    b = synth.make_nms_boxes(seed, n)
+    keep = nms(torch.from_numpy(b).to(DEV), thr).cpu().numpy()
+    want = oracle.nms3d(b, thr, fma_mode=1)  # the reference's CUDA arithmetic
+    assert np.array_equal(keep, want)
+    # the numpy (CPU-reference) arithmetic may differ by one ulp at the threshold only
+    want_cpu = oracle.nms3d(b, thr, fma_mode=0)
+    iou = oracle.iou_matrix(b, 0)
+    if np.abs(iou - np.float32(thr)).min() > 1e-6:
+        assert np.array_equal(keep, want_cpu)
+
+
+def test_nms_matches_golden_reference_cpu_nms(oracle):
+    from lib.layer_utils.nms_wrapper import nms
+    g = load_golden("operators.npz")
+    for seed in range(6):
+        s, n, thr = g[f"nms_cfg_{seed}"]
+        b = synth.make_nms_boxes(int(s), int(n))
+        keep = nms(torch.from_numpy(b).to(DEV), float(thr)).cpu().numpy()
+        assert np.array_equal(keep, g[f"nms_keep_{seed}"])
+
+
+def test_nms_edge_cases(oracle):
+    from lib.layer_utils.nms_wrapper import nms
+    assert nms(torch.zeros(0, 6, device=DEV), 0.5).numel() == 0
+    same = np.tile(np.array([[1, 2, 3, 9, 9, 9]], np.float32), (130, 1))
+    assert nms(torch.from_numpy(same).to(DEV), 0.5).cpu().tolist() == [0]
+    far = np.stack([np.array([i * 20, 0, 0, i * 20 + 5, 5, 5], np.float32) for i in range(70)])
+    assert nms(torch.from_numpy(far).to(DEV), 0.1).cpu().tolist() == list(range(70))
+
+
+def test_nms_mask_vs_reference_cuda_kernel(oracle):
+    """Bitmask of the reference's own kernel (compiled unmodified into oracle/_ref) == ours -> same keep."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_nms_cuda.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built")
+    ref = C.CDLL(path)
+    for seed, n, thr in ((0, 400, 0.1), (7, 777, 0.25)):
+        b = synth.make_nms_boxes(seed, n)
+        bd = torch.from_numpy(b).to(DEV)
+        cb = (n + 63) // 64
+        mask = torch.zeros(n, cb, dtype=torch.int64, device=DEV)
+        torch.cuda.synchronize()
+        ref._nms(C.c_int(n), C.c_void_p(bd.data_ptr()), C.c_void_p(mask.data_ptr()), C.c_float(thr))
+        torch.cuda.synchronize()
+        m = mask.cpu().numpy().view(np.uint64)
+        remv = np.zeros(cb, np.uint64)
+        keep = []
+        for i in range(n):  # host reduce of lib/layer_utils/nms/src/nms_cuda.c:41-59
+            if not (remv[i // 64] >> np.uint64(i % 64)) & np.uint64(1):
+                keep.append(i)
+                remv[i // 64:] |= m[i, i // 64:]
+        from lib.layer_utils.nms_wrapper import nms
+        assert nms(bd, thr).cpu().tolist() == keep
+
+
+# ---------------------------------------------------------------- RoI pooling
+def _roi_inputs(seed=11, C_=16, dims=(24, 12, 24), n=40):
+    rng = np.random.default_rng(seed)
+    feat = rng.standard_normal((1, C_) + dims).astype(np.float32)
+    rois = synth.make_nms_boxes(seed + 10, n)
+    rois[0] = [5, 5, 5, 5, 5, 5]
+    rois[1] = [90, 40, 90, 96, 48, 96]
+    rois[2] = [0, 0, 0, 96, 48, 96]
+    rois[3] = [10.5, 3.25, 7.75, 11.0, 3.5, 8.0]
+    return feat, rois
+
+
+@pytest.mark.parametrize("C_,pool", [(16, 4), (128, 4), (130, 2), (8, 3)])
+def test_roi_pool_exact_both_layouts(oracle, S, C_, pool):
+    from lib.layer_utils.roi_pooling.roi_pool import RoIPoolFunction
+    feat, rois = _roi_inputs(C_=C_)
+    want, warg = oracle.roi_pool3d(feat, rois, (pool,) * 3, 0.25)
+    fn = RoIPoolFunction(pool, pool, pool, 0.25)
+    out = fn(torch.from_numpy(feat).to(DEV), torch.from_numpy(rois).to(DEV))
+    assert np.array_equal(out.cpu().numpy(), want)
+    assert np.array_equal(fn.argmax.cpu().numpy(), warg)
+    # VC layout, pyramid form (level 1 -> feat, level 2 -> -feat, id 0 -> zeros)
+    fvc = torch.from_numpy(feat[0]).to(DEV).permute(1, 2, 3, 0).contiguous()
+    n = rois.shape[0]
+    lv = torch.ones(n, dtype=torch.int32, device=DEV)
+    lv[1::3] = 2
+    lv[2::5] = 0
+    top = torch.empty(n, C_ * pool ** 3, device=DEV)
+    arg = torch.empty(n, C_ * pool ** 3, dtype=torch.int32, device=DEV)
+    S.check(S.lib.sis3d_roi_pool_levels(S.ptr(fvc), S.ptr((-fvc).contiguous()), None, S.ptr(lv), S.f32(0.25), n, 24, 12, 24,
+                                        C_, pool, pool, pool, S.ptr(torch.from_numpy(rois).to(DEV)), S.ptr(top), S.ptr(arg),
+                                        S.stream()))
+    want2, warg2 = oracle.roi_pool3d(-feat, rois, (pool,) * 3, 0.25)
+    lvh = lv.cpu().numpy()
+    got = top.cpu().numpy().reshape(want.shape)
+    garg = arg.cpu().numpy().reshape(want.shape)
+    assert np.array_equal(got[lvh == 1], want[lvh == 1]) and np.array_equal(garg[lvh == 1], warg[lvh == 1])
+    assert np.array_equal(got[lvh == 2], want2[lvh == 2]) and np.array_equal(garg[lvh == 2], warg2[lvh == 2])
+    assert not got[lvh == 0].any()
+
+
+def test_roi_pool_golden_and_reference_cuda(oracle):
+    from lib.layer_utils.roi_pooling.roi_pool import RoIPoolFunction
+    g = load_golden("operators.npz")
+    feat = np.random.default_rng(11).standard_normal((1, 16, 24, 12, 24)).astype(np.float32)
+    fd, rd = torch.from_numpy(feat).to(DEV), torch.from_numpy(g["roi_rois"]).to(DEV)
+    fn = RoIPoolFunction(4, 4, 4, 0.25)
+    out = fn(fd, rd)
+    assert np.array_equal(out.cpu().numpy(), g["roi_out"])  # reference CPU C kernel
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_roi_cuda.so")
+    if os.path.exists(path):
+        ref = C.CDLL(path)
+        top = torch.zeros_like(out)
+        arg = torch.zeros(out.shape, dtype=torch.int32, device=DEV)
+        torch.cuda.synchronize()
+        ref.ROIPoolForwardLaucher(C.c_void_p(fd.data_ptr()), C.c_float(0.25), rd.shape[0], 24, 12, 24, 16, 4, 4, 4,
+                                  C.c_void_p(rd.data_ptr()), C.c_void_p(top.data_ptr()), C.c_void_p(arg.data_ptr()),
+                                  C.c_void_p(0))
+        torch.cuda.synchronize()
+        assert torch.equal(top, out) and torch.equal(arg, fn.argmax)
+
+
+# ---------------------------------------------------------------- convolution / pooling
+CONV_CASES = [  # cin, cout, ks, stride, dims, bias, res, act
+    (2, 32, 2, 2, (13, 9, 11), False, False, 1), (32, 32, 1, 1, (7, 5, 6), True, False, 1),
+    (32, 32, 3, 1, (9, 6, 7), True, False, 1), (32, 64, 1, 1, (6, 5, 7), True, True, 1),
+    (128, 64, 2, 2, (8, 6, 10), False, False, 1), (128, 128, 3, 1, (6, 5, 7), False, False, 1),
+    (128, 256, 3, 1, (5, 4, 6), True, False, 1), (256, 22, 1, 1, (5, 4, 6), True, False, 0),
+    (256, 66, 1, 1, (5, 4, 6), True, False, 0), (2, 64, 3, 1, (7, 9, 5), False, False, 1),
+    (64, 19, 1, 1, (7, 3, 5), False, False, 2), (64, 64, 3, 1, (70, 3, 3), False, False, 1)]
+
+
+@pytest.mark.parametrize("cin,cout,ks,stride,dims,bias,res,act", CONV_CASES)
+def test_conv3d_vs_torch_fp32(S, cin, cout, ks, stride, dims, bias, res, act):
+    rng = np.random.default_rng(cin * 1000 + cout + ks)
+    x = rng.standard_normal((1, cin) + dims).astype(np.float32)
+    w = (rng.standard_normal((cout, cin, ks, ks, ks)) / np.sqrt(cin * ks ** 3)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32) if bias else None
+    pad = 1 if ks == 3 else 0
+    ref = F.conv3d(torch.from_numpy(x), torch.from_numpy(w), None if b is None else torch.from_numpy(b), stride=stride,
+                   padding=pad)
+    r = rng.standard_normal(tuple(ref.shape)).astype(np.float32) if res else None
+    if res:
+        ref = ref + torch.from_numpy(r)
+    ref = F.relu(ref) if act == 1 else (torch.sigmoid(ref) if act == 2 else ref)
+    od = tuple(ref.shape[2:])
+    xd = torch.from_numpy(x[0]).to(DEV).permute(1, 2, 3, 0).contiguous()  # VC
+    wd = torch.from_numpy(w).to(DEV)
+    ldw = (cout + 3) // 4 * 4
+    packed = torch.empty(ks ** 3 * cin, ldw, device=DEV)
+    S.check(S.lib.sis3d_pack_conv_weight(S.ptr(wd), cout, cin, ks, S.ptr(packed), S.stream()))
+    out = torch.full(od + (cout + 4,), 7.0, device=DEV)  # write into a wider tensor at channel offset 4
+    X, Y, Z = dims
+    for layout in ("vc", "ncdhw"):
+        if layout == "vc":
+            inp, strides, sc = xd, (Y * Z * cin, Z * cin, cin), 1
+        else:
+            inp, strides, sc = torch.from_numpy(x[0]).to(DEV).contiguous(), (Y * Z, Z, 1), X * Y * Z
+        regions, tiles = S.make_regions([dict(in_off=0, out_off=0, in_dim=dims, out_dim=od, in_stride=strides)], DEV)
+        rd = torch.from_numpy(r[0]).to(DEV).permute(1, 2, 3, 0).contiguous() if res else None
+        S.check(S.lib.sis3d_conv3d(S.ptr(inp), C.c_int64(sc), S.ptr(packed), S.ptr(torch.from_numpy(b).to(DEV)) if bias else None,
+                                   S.ptr(rd), cout if res else 0, 0, S.ptr(out), cout + 4, 4, S.ptr(regions), 1, tiles, cin,
+                                   cout, ks, stride, pad, act, S.stream()))
+        got = out[..., 4:].permute(3, 0, 1, 2).cpu()
+        assert torch.all(out[..., :4] == 7.0)
+        torch.testing.assert_close(got, ref[0], atol=2e-5, rtol=1e-4)
+
+
+def test_conv3d_regions_zero_pad_at_crop_border(S):
+    """Two crops of one NCDHW scene in a single launch == conv of each crop with zero padding."""
+    rng = np.random.default_rng(5)
+    X, Y, Z = 20, 12, 16
+    scene = rng.standard_normal((1, 2, X, Y, Z)).astype(np.float32)
+    w = (rng.standard_normal((64, 2, 3, 3, 3)) / 7).astype(np.float32)
+    crops = [(2, 1, 3, 9, 8, 10), (5, 0, 0, 20, 12, 7)]
+    sd = torch.from_numpy(scene).to(DEV)
+    packed = torch.empty(54, 64, device=DEV)
+    S.check(S.lib.sis3d_pack_conv_weight(S.ptr(torch.from_numpy(w).to(DEV)), 64, 2, 3, S.ptr(packed), S.stream()))
+    sizes = [(c[3] - c[0], c[4] - c[1], c[5] - c[2]) for c in crops]
+    offs = np.concatenate([[0], np.cumsum([a * b * c for a, b, c in sizes])])
+    out = torch.empty(int(offs[-1]) * 64, device=DEV)
+    regions, tiles = S.make_regions([dict(in_off=(c[0] * Y + c[1]) * Z + c[2], out_off=int(offs[j]) * 64, in_dim=s, out_dim=s,
+                                          in_stride=(Y * Z, Z, 1)) for j, (c, s) in enumerate(zip(crops, sizes))], DEV)
+    S.check(S.lib.sis3d_conv3d(S.ptr(sd), C.c_int64(X * Y * Z), S.ptr(packed), None, None, 0, 0, S.ptr(out), 64, 0,
+                               S.ptr(regions), 2, tiles, 2, 64, 3, 1, 1, 1, S.stream()))
+    for j, (c, s) in enumerate(zip(crops, sizes)):
+        ref = F.relu(F.conv3d(torch.from_numpy(scene[:, :, c[0]:c[3], c[1]:c[4], c[2]:c[5]]), torch.from_numpy(w), padding=1))[0]
+        got = out[int(offs[j]) * 64:int(offs[j + 1]) * 64].view(*s, 64).permute(3, 0, 1, 2).cpu()
+        torch.testing.assert_close(got, ref, atol=2e-5, rtol=1e-4)
+
+
+def test_maxpool3_exact(S):
+    x = torch.randn(1, 64, 9, 5, 7)
+    ref = F.max_pool3d(x, 3, 1, 1)[0]
+    xd = x[0].to(DEV).permute(1, 2, 3, 0).contiguous()
+    out = torch.zeros(9, 5, 7, 128, device=DEV)
+    S.check(S.lib.sis3d_maxpool3(S.ptr(xd), S.ptr(out), 128, 64, 9, 5, 7, 64, S.stream()))
+    assert torch.equal(out[..., 64:].permute(3, 0, 1, 2).cpu(), ref)
+    assert not out[..., :64].any()
+
+
+# ---------------------------------------------------------------- projection
+def _views(dims, n_img, seed):
+    data, boxes = synth.make_scene(seed, dims)
+    return synth.make_views(seed, dims, n_img, boxes)
+
+
+@pytest.mark.parametrize("tag,dims,n_img,seed", [("odd_45x27x41", (45, 27, 41), 3, 202), ("cfg2_96x48x96", (96, 48, 96), 5, 303)])
+def test_compute_projection_index_lists_exact(oracle, tag, dims, n_img, seed):
+    from lib.layer_utils.projection import ProjectionHelper
+    g = load_golden(f"forward_{tag}.npz")
+    cfg = oracle.make_cfg("scannet")
+    v = _views(dims, n_img, seed)
+    helper = ProjectionHelper(cfg.INTRINSIC, cfg.PROJ_DEPTH_MIN, cfg.PROJ_DEPTH_MAX, cfg.DEPTH_SHAPE, dims, cfg.VOXEL_SIZE)
+    for i in range(n_img):
+        m = helper.compute_projection(torch.from_numpy(v["depths"][i]).to(DEV), torch.from_numpy(v["poses"][i]),
+                                      torch.from_numpy(v["world2grid"]))
+        assert m is not None
+        k = int(m[0][0].item())
+        assert k == len(g[f"proj3d_{i}"]), f"view {i}: {k} vs {len(g[f'proj3d_{i}'])}"
+        assert np.array_equal(m[0][1:1 + k].cpu().numpy(), g[f"proj3d_{i}"])
+        assert np.array_equal(m[1][1:1 + k].cpu().numpy(), g[f"proj2d_{i}"])
+
+
+def test_compute_projection_none_when_nothing_valid(oracle):
+    from lib.layer_utils.projection import ProjectionHelper
+    cfg = oracle.make_cfg("scannet")
+    dims = (16, 16, 16)
+    helper = ProjectionHelper(cfg.INTRINSIC, cfg.PROJ_DEPTH_MIN, cfg.PROJ_DEPTH_MAX, cfg.DEPTH_SHAPE, dims, cfg.VOXEL_SIZE)
+    v = _views(dims, 1, 1)
+    depth = torch.full((32, 41), 9.0)  # beyond depth_max everywhere
+    assert helper.compute_projection(depth.to(DEV), torch.from_numpy(v["poses"][0]), torch.from_numpy(v["world2grid"])) is None
+    assert oracle.compute_projection(cfg, depth, v["poses"][0], v["world2grid"], dims) is None
+
+
+def test_projection_apply_and_running_max(oracle):
+    from lib.layer_utils.projection import Projection, ProjectionHelper
+    cfg = oracle.make_cfg("scannet")
+    dims, n_img = (45, 27, 41), 3
+    v = _views(dims, n_img, 202)
+    helper = ProjectionHelper(cfg.INTRINSIC, cfg.PROJ_DEPTH_MIN, cfg.PROJ_DEPTH_MAX, cfg.DEPTH_SHAPE, dims, cfg.VOXEL_SIZE)
+    for i in range(n_img):
+        m = helper.compute_projection(torch.from_numpy(v["depths"][i]).to(DEV), torch.from_numpy(v["poses"][i]),
+                                      torch.from_numpy(v["world2grid"]))
+        got = Projection.apply(torch.from_numpy(v["feats"][i]).to(DEV), m[0], m[1], dims)
+        l3, l2 = oracle.compute_projection(cfg, v["depths"][i], v["poses"][i], v["world2grid"], dims)
+        want = oracle.projection_scatter(v["feats"][i], l3, l2, dims)
+        assert torch.equal(got.cpu(), want)
+
+
+# ---------------------------------------------------------------- proposals
+@pytest.mark.parametrize("dims,seed", [((24, 12, 24), 1), ((11, 7, 10), 2), ((8, 8, 8), 3)])
+def test_rpn_proposals_vs_oracle(oracle, dims, seed):
+    """Same logits/deltas in -> same top-N order, same NMS keep, boxes within float tolerance."""
+    from lib.layer_utils.proposal_layer import rpn_proposals
+    from lib.utils.config import cfg, cfg_from_file, cfg_reset
+    cfg_reset()
+    cfg_from_file(os.path.join(ROOT, "3d-sis_b200", "experiments", "cfgs", "ScanNet", "rpn_class_mask_5.yml"))
+    ocfg = oracle.make_cfg("scannet")
+    rng = np.random.default_rng(seed)
+    scene = tuple(4 * d for d in dims)
+    levels, olevels = [], []
+    for A, tab in ((3, "scannet14_3.txt"), (11, "scannet14_11.txt")):
+        n = dims[0] * dims[1] * dims[2]
+        cls = (rng.standard_normal((n, 2 * A)) * 2).astype(np.float32)
+        dl = (rng.standard_normal((n, 6 * A)) * 0.2).astype(np.float32)
+        sizes = oracle.read_anchor_table(tab)
+        levels.append(dict(cls=torch.from_numpy(cls).to(DEV), deltas=torch.from_numpy(dl).to(DEV),
+                           sizes=torch.tensor(sizes, dtype=torch.float32, device=DEV), grid=dims, A=A, cls_mode=0))
+        logits = torch.from_numpy(cls).view(n, 2, A)
+        prob = F.softmax(logits, dim=1)[:, 1, :].reshape(-1)
+        olevels.append((prob, torch.from_numpy(dl).view(-1, 6), oracle.generate_anchors(dims, sizes, 4)))
+    want = oracle.proposal_layer(ocfg, olevels, scene, fma_mode=1)
+    rois, scores, lvl, num, order = rpn_proposals(levels, scene, "TEST", want_order=True)
+    n = int(num.item())
+    # flat index (level, voxel, a) of the oracle's order: oracle indices are into the inside-compacted list
+    inside = np.concatenate([oracle.inside_mask(l[2], scene) for l in olevels])
+    flat_of_compact = np.nonzero(inside)[0]
+    want_flat = flat_of_compact[want["order"]]
+    got_flat = order.cpu().numpy()[:len(want_flat)]
+    sc = want["all_scores"]
+    if not np.array_equal(got_flat, want_flat):
+        # only allowed difference: scores that differ by < 1 ulp-ish between expf implementations
+        diff = np.nonzero(got_flat != want_flat)[0]
+        s_sorted = sc[want["order"]]
+        assert np.all(np.abs(s_sorted[diff] - s_sorted[np.clip(diff + 1, 0, len(s_sorted) - 1)]) < 1e-6) or \
+            np.all(np.abs(s_sorted[diff] - s_sorted[np.clip(diff - 1, 0, len(s_sorted) - 1)]) < 1e-6)
+        pytest.skip("top-N order differs only among near-tied scores")
+    assert n == len(want["rois"])
+    np.testing.assert_allclose(rois[:n].cpu().numpy(), want["rois"].numpy(), atol=1e-4, rtol=1e-5)
+    np.testing.assert_allclose(scores[:n].cpu().numpy(), want["scores"].numpy(), atol=1e-6)
+    assert np.array_equal(lvl[:n].cpu().numpy(), want["level_inds"].numpy().astype(np.int32))
+    assert not rois[n:].any()
+
+
+def test_rpn_proposals_few_candidates(oracle):
+    """Fewer inside anchors than pre_top_n (empty-ish edge case, SURVEY appendix A: SUNCG 32^3 level 2)."""
+    from lib.layer_utils.proposal_layer import rpn_proposals
+    from lib.utils.config import cfg, cfg_from_file, cfg_reset
+    cfg_reset()
+    cfg_from_file(os.path.join(ROOT, "3d-sis_b200", "experiments", "cfgs", "SUNCG", "rpn_class_mask_5.yml"))
+    ocfg = oracle.make_cfg("suncg")
+    dims, scene = (8, 8, 8), (32, 32, 32)
+    rng = np.random.default_rng(9)
+    levels, olevels = [], []
+    for A, tab in ((3, "suncg9_3.txt"), (6, "suncg9_6.txt")):
+        n = 512
+        cls = rng.standard_normal((n, 2 * A)).astype(np.float32)
+        dl = (rng.standard_normal((n, 6 * A)) * 0.1).astype(np.float32)
+        sizes = oracle.read_anchor_table(tab)
+        levels.append(dict(cls=torch.from_numpy(cls).to(DEV), deltas=torch.from_numpy(dl).to(DEV),
+                           sizes=torch.tensor(sizes, dtype=torch.float32, device=DEV), grid=dims, A=A, cls_mode=0))
+        prob = F.softmax(torch.from_numpy(cls).view(n, 2, A), dim=1)[:, 1, :].reshape(-1)
+        olevels.append((prob, torch.from_numpy(dl).view(-1, 6), oracle.generate_anchors(dims, sizes, 4)))
+    assert oracle.inside_mask(olevels[1][2], scene).sum() == 0  # level 2 contributes nothing
+    want = oracle.proposal_layer(ocfg, olevels, scene, fma_mode=1)
+    rois, scores, lvl, num = rpn_proposals(levels, scene, "TEST")
+    n = int(num.item())
+    assert n == len(want["rois"])
+    np.testing.assert_allclose(rois[:n].cpu().numpy(), want["rois"].numpy(), atol=1e-4)
