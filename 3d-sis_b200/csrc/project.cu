@@ -213,15 +213,15 @@ __global__ void __launch_bounds__(256) backproject_max_kernel(const float *feats
 using namespace sis3d;
 
 extern "C" int sis3d_project_map(const float *views, const float *depth, int n_views, int img_w, int img_h,
-                                 const float *intr, float depth_min, float depth_max, float voxel_size, int X, int Y,
+                                 float fx, float fy, float cx, float cy, float depth_min, float depth_max, float voxel_size, int X, int Y,
                                  int Z, int16_t *pix, int32_t *counts, void *stream) {
-    if (!views || !depth || !intr || !pix || !counts || n_views <= 0 || img_w * img_h > 32767) return SIS3D_EINVAL;
+    if (!views || !depth || !pix || !counts || n_views <= 0 || img_w * img_h > 32767) return SIS3D_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
     if (cudaMemsetAsync(counts, 0, sizeof(int32_t) * n_views, s) != cudaSuccess) return SIS3D_ELAUNCH;
     const int64_t n0 = (int64_t)X * Y * Z;
     dim3 grid((unsigned)imin64(cdiv64(n0, 256), 148 * 8), n_views);
-    project_map_kernel<<<grid, 256, 0, s>>>((const ViewParams *)views, depth, img_w, img_h, intr[0], intr[1], intr[2],
-                                            intr[3], depth_min, depth_max, voxel_size, X, Y, Z, pix, counts);
+    project_map_kernel<<<grid, 256, 0, s>>>((const ViewParams *)views, depth, img_w, img_h, fx, fy, cx,
+                                            cy, depth_min, depth_max, voxel_size, X, Y, Z, pix, counts);
     return finish_launch();
 }
 

@@ -53,15 +53,15 @@ def view_params(intrinsic, image_dims, depth_min, depth_max, volume_dims, depths
     return out
 
 
-def project_maps(views_dev, depths_dev, intr_dev, cfgvals, volume_dims, img_w, img_h):
+def project_maps(views_dev, depths_dev, intr, cfgvals, volume_dims, img_w, img_h):
     """Launch sis3d_project_map for all views: returns (pix int16 [n,N0], counts int32 [n]) on device."""
     X, Y, Z = (int(v) for v in volume_dims)
     n = views_dev.shape[0]
     pix = torch.empty(n, X * Y * Z, dtype=torch.int16, device=views_dev.device)
     counts = torch.empty(n, dtype=torch.int32, device=views_dev.device)
     dmin, dmax, vs = cfgvals
-    S.check(S.lib.sis3d_project_map(S.ptr(views_dev), S.ptr(depths_dev), n, img_w, img_h, S.ptr(intr_dev),
-                                    S.f32(dmin), S.f32(dmax), S.f32(vs), X, Y, Z, S.ptr(pix), S.ptr(counts), S.stream()),
+    S.check(S.lib.sis3d_project_map(S.ptr(views_dev), S.ptr(depths_dev), n, img_w, img_h, S.f32(intr[0]), S.f32(intr[1]),
+                                    S.f32(intr[2]), S.f32(intr[3]), S.f32(dmin), S.f32(dmax), S.f32(vs), X, Y, Z, S.ptr(pix), S.ptr(counts), S.stream()),
             "project_map")
     return pix, counts
 
@@ -79,8 +79,7 @@ class ProjectionHelper:
         w, h = int(self.image_dims[0]), int(self.image_dims[1])
         vp = view_params(self.intrinsic, (w, h), self.depth_min, self.depth_max, (X, Y, Z), None,
                          camera_to_world, world_to_grid).to(dev)
-        intr = torch.tensor([self.intrinsic[0][0], self.intrinsic[1][1], self.intrinsic[0][2], self.intrinsic[1][2]],
-                            dtype=torch.float32, device=dev)
+        intr = (self.intrinsic[0][0], self.intrinsic[1][1], self.intrinsic[0][2], self.intrinsic[1][2])
         d = depth.to(dev, torch.float32).contiguous().reshape(1, h, w)
         pix, counts = project_maps(vp, d, intr, (self.depth_min, self.depth_max, self.voxel_size), (X, Y, Z), w, h)
         if int(counts[0].item()) == 0:

@@ -64,6 +64,7 @@ class Network(nn.Module):
         self._region_cache = {}
         self._const_cache = {}
         self._keep_debug = False
+        self._prof = None  # name -> [(start_event, end_event)] when per-kernel timing is on (bench.py)
 
     # ------------------------------------------------------------------ parameters
     def _declare_conv(self, name, cout, cin, ks, bias):
@@ -142,6 +143,20 @@ class Network(nn.Module):
         torch.cuda.current_stream().synchronize()
         self._packed_version = v
 
+    # ------------------------------------------------------------------ per-kernel timing hooks
+    def _rec(self, name):
+        if self._prof is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return name, e
+
+    def _rec_end(self, tok):
+        if tok is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._prof.setdefault(tok[0], []).append((tok[1], e))
+
     # ------------------------------------------------------------------ primitive ops
     def _regions_single(self, x: Act, out_dims, stride):
         key = ("single", x.dims, x.C, x.layout, x.ld, tuple(out_dims), stride)
@@ -171,12 +186,14 @@ class Network(nn.Module):
             out = Act(torch.empty(*out_dims, cout, dtype=torch.float32, device=x.t.device), out_dims, cout)
         in_sc = 1 if x.layout == "vc" else x.nvox
         xin = x.t if x.coff == 0 else x.t.reshape(-1)[x.coff:]
+        tok = self._rec(f"conv[{name}]")
         S.check(S.lib.sis3d_conv3d(S.ptr(xin), C.c_int64(in_sc), S.ptr(packed), S.ptr(bias),
                                    S.ptr(residual.t) if residual is not None else None,
                                    residual.ld if residual is not None else 0,
                                    residual.coff if residual is not None else 0,
                                    S.ptr(out.t), out.ld, out.coff, S.ptr(regions), regions.numel() // S.REGION_BYTES,
                                    n_tiles, cin, cout, ks, stride, pad, act, S.stream()), f"conv3d[{name}]")
+        self._rec_end(tok)
         return out
 
     def _bottleneck(self, x: Act, name, out: Act = None):
@@ -190,7 +207,9 @@ class Network(nn.Module):
             out = Act(torch.empty(*x.dims, x.C, dtype=torch.float32, device=x.t.device), x.dims, x.C)
         if x.ld != x.C or x.coff:
             raise S.Sis3dError("maxpool3 expects a dense VC input")
+        tok = self._rec("maxpool3")
         S.check(S.lib.sis3d_maxpool3(S.ptr(x.t), S.ptr(out.t), out.ld, out.coff, *x.dims, x.C, S.stream()), "maxpool3")
+        self._rec_end(tok)
         return out
 
     def _run_stack(self, x: Act, prefix, spec, final_out=None):
@@ -249,16 +268,18 @@ class Network(nn.Module):
             vp = proj.view_params(cfg.INTRINSIC, (w, h), cfg.PROJ_DEPTH_MIN, cfg.PROJ_DEPTH_MAX, dims,
                                   None, imgs["poses"][0], imgs["world2grid"][0]).to(dev, non_blocking=True)
             depths = torch.as_tensor(imgs["depths"][0]).to(dev, torch.float32, non_blocking=True).contiguous()
-            intr = self._const(("intr", dev), lambda: torch.tensor(
-                [cfg.INTRINSIC[0][0], cfg.INTRINSIC[1][1], cfg.INTRINSIC[0][2], cfg.INTRINSIC[1][2]],
-                dtype=torch.float32, device=dev))
+            intr = (cfg.INTRINSIC[0][0], cfg.INTRINSIC[1][1], cfg.INTRINSIC[0][2], cfg.INTRINSIC[1][2])
+            tok = self._rec("project_map")
             pix, counts = proj.project_maps(vp, depths, intr, (cfg.PROJ_DEPTH_MIN, cfg.PROJ_DEPTH_MAX, cfg.VOXEL_SIZE),
                                             dims, w, h)
+            self._rec_end(tok)
             pairs = torch.empty(3 * n, dtype=torch.int32, device=dev)
             n_pairs = torch.empty(1, dtype=torch.int32, device=dev)
             S.check(S.lib.sis3d_backproject_pairs(S.ptr(counts), n, S.ptr(pairs), S.ptr(n_pairs), S.stream()), "pairs")
             self._proj_counts = counts
+        tok = self._rec("backproject_max")
         vol = proj.backproject(feats, pix, pairs, n_pairs, dims, w, h)
+        self._rec_end(tok)
         return Act(vol, dims, feats.shape[1])
 
     def _backbone(self, scene: Act, imageft: Act):
@@ -297,7 +318,9 @@ class Network(nn.Module):
             if self._keep_debug:
                 self._predictions[f"rpn_cls_logits_level{lvl}"] = cls.t
                 self._predictions[f"rpn_bbox_pred_level{lvl}"] = bbox.t
+        tok = self._rec("rpn_proposals")
         res = rpn_proposals(levels, dims, "TEST", want_order=self._keep_debug)
+        self._rec_end(tok)
         if self._keep_debug:
             self._predictions["rpn_order"] = res[4]
         return res[:4]
@@ -311,9 +334,11 @@ class Network(nn.Module):
         dev = rois.device
         pool5 = torch.empty(R, f1.C * P ** 3, dtype=torch.float32, device=dev)
         f = [x.t if x is not None else None for x in feats] + [None, None]
+        tok = self._rec("roi_pool_levels")
         S.check(S.lib.sis3d_roi_pool_levels(S.ptr(f[0]), S.ptr(f[1]), S.ptr(f[2]), S.ptr(level_ids),
                                             S.f32(1.0 / self._feat_stride[0]), R, *f1.dims, f1.C, P, P, P, S.ptr(rois),
                                             S.ptr(pool5), None, S.stream()), "roi_pool_levels")
+        self._rec_end(tok)
         x = Act(pool5, (R, 1, 1), pool5.shape[1])
         for i in (0, 2, 4):
             x = self._conv(x, f"classifier.{i}", act=1)

@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py -- scenes/sec of the 3D-SIS dense-voxel TEST forward on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step = one pass of the hot path (back-projection -> 3D backbone -> RPN/NMS -> RoI pool + classifier
+-> per-RoI mask head) over one synthetic 96x48x96 ScanNet-shape chunk with 5 views
+(BASELINE.json configs[1]); ENet-shaped 2D features are an input (ENet is upstream of the path,
+SURVEY 8f2).  One process per GPU; chunks are independent so ranks shard with no data-path
+collective ("weak" scaling: K chunks per rank); NCCL carries only the barrier and the max-over-ranks
+time.  `value` times the forward with inputs resident in HBM, `e2e` the same call from pinned HOST
+buffers including the result read-back.  See the task contract in DESIGN.md "measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "3d-sis_b200"), ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+DIMS, N_IMG = (96, 48, 96), 5
+ALG_BYTES = 806.8e6       # per-layer compulsory fp32 bytes, backbone + RPN, cfg2
+MASK_BYTES_PER_VOXEL = 2712.0
+METRIC = "scenes_per_sec_96x48x96_5img"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "measured"
+    except Exception:
+        return 6650.0, 1590.0, "fallback"
+
+
+def case(seed):
+    import sis3d_synth as synth
+    data, boxes = synth.make_scene(seed, DIMS)
+    views = synth.make_views(seed, DIMS, N_IMG, boxes)
+    return data, views
+
+
+def weights():
+    import sis3d_synth as synth
+    return synth.make_weights(seed=0)
+
+
+class Clocks(threading.Thread):
+    """nvidia-smi clock / throttle sampling during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([t.strip() for t in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port: the reference
+    Python files cannot travel to the GPU box), all host threads, rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = port.make_cfg("scannet")
+    w = weights()
+    data, views = case(303)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        port.forward(cfg, w, data, views)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+        if sum(times) > 150:  # bounded sample
+            break
+    ms = 1e3 * float(np.mean(times))
+    v = 1e3 / ms
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "scenes/s", "n_gpus": args.gpus, "steps": len(times),
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "96x48x96 ScanNet-shape chunk, 5 views, full rpn_class_mask_5 TEST forward (cfg2)",
+                   "weights": "seeded synthetic", "threads": cores},
+        "cpu_baseline": {"value": v, "unit": "scenes/s", "cores": cores, "kind": "port",
+                         "sample": f"{len(times)} full chunks, torch-CPU fp32 oracle port of the reference path"},
+        "e2e": {"value": v, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="sis3d")
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from lib import _sis3d as S
+    from test_gpu_forward import make_net
+    from test_oracle_golden import CASES
+    net, cfg = make_net(CASES["cfg2_96x48x96"], keep_debug=False)
+
+    # distinct chunk per rank and per step slot (4 rotating inputs per rank)
+    n_in = 4
+    host_in, dev_in = [], []
+    for j in range(n_in):
+        data, views = case(1000 + rank * 16 + j)
+        hb = {"data": torch.from_numpy(data).pin_memory(), "id": ["bench"],
+              "nearest_images": {k2: [torch.from_numpy(views[k1]).pin_memory()] for k1, k2 in
+                                 (("feats", "images"), ("depths", "depths"), ("poses", "poses"), ("world2grid", "world2grid"))}}
+        host_in.append(hb)
+        db = {"data": hb["data"].to(dev), "id": ["bench"],
+              "nearest_images": {"images": [hb["nearest_images"]["images"][0].to(dev)],
+                                 "depths": [hb["nearest_images"]["depths"][0].to(dev)],
+                                 "poses": hb["nearest_images"]["poses"], "world2grid": hb["nearest_images"]["world2grid"]}}
+        dev_in.append(db)
+    h2d = sum(t.numel() * t.element_size() for t in [host_in[0]["data"]] + [v[0] for v in host_in[0]["nearest_images"].values()])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(blobs, readback):
+        P = net.forward(blobs, "TEST", None)
+        nbytes = 0
+        if readback:
+            det = P["detections_host"]
+            nbytes += det.nbytes
+            for m, row in zip(P["mask_pred"][0], det[det[:, 8] > 0.5]):
+                hm = m[0, int(row[7])].cpu()
+                nbytes += hm.numel() * 4
+        return P, nbytes
+
+    def timed(inputs, readback, steps):
+        evs, launches0, d2h, vox, nroi, nmask = [], S.launch_count(), 0, 0, 0, 0
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        for i in range(steps):
+            flush.fill_(i & 255)  # L2 flush between timed iterations (not timed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            P, nb = step(inputs[i % n_in], readback)
+            e1.record()
+            evs.append((e0, e1))
+            d2h += nb
+            det = P["detections_host"]
+            k = det[det[:, 8] > 0.5]
+            vox += int(((k[:, 12] - k[:, 9]) * (k[:, 13] - k[:, 10]) * (k[:, 14] - k[:, 11])).sum())
+            nroi += det.shape[0]
+            nmask += k.shape[0]
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), S.launch_count() - launches0, d2h / steps, vox / steps, nroi / steps, nmask / steps
+
+    for i in range(args.warmup):
+        step(dev_in[i % n_in], False)
+        step(host_in[i % n_in], True)
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    ms_dev, launches, _, vox, nroi, nmask = timed(dev_in, False, args.steps)
+    ms_e2e, _, d2h, _, _, _ = timed(host_in, True, args.steps)
+    clocks.stop_flag = True
+
+    # per-kernel device time of the dominant kernel family, CUDA events on the launching stream
+    net._prof = {}
+    for i in range(min(args.steps, 5)):
+        step(dev_in[i % n_in], False)
+    torch.cuda.synchronize()
+    prof = {k: (sum(a.elapsed_time(b) for a, b in v) / min(args.steps, 5), len(v) // min(args.steps, 5)) for k, v in net._prof.items()}
+    net._prof = None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm, tflops, which = peaks()
+    per_step_ms = ms_dev / args.steps
+    value = world * args.steps / (ms_dev / 1e3)
+    e2e_v = world * args.steps / (ms_e2e / 1e3)
+    conv_ms = sum(v[0] for k, v in prof.items() if k.startswith("conv"))
+    top = sorted(prof.items(), key=lambda kv: -kv[1][0])[:6]
+    alg = ALG_BYTES + MASK_BYTES_PER_VOXEL * vox
+    kernel_ms = sum(v[0] for v in prof.values())
+    out = {
+        "metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "96x48x96 ScanNet-shape chunk, 5 views, full rpn_class_mask_5 TEST forward (cfg2)",
+                   "inputs": "seeded synthetic TSDF + ENet-shaped features/depth/poses; seeded synthetic weights",
+                   "l2": "256 MiB flush write between timed iterations (untimed)", "rois_per_step": nroi,
+                   "mask_rois_per_step": nmask, "mask_voxels_per_step": vox, "chunks_per_rank": args.steps,
+                   "parallelism": f"chunk-sharded dp{world}"},
+        "e2e": {"value": e2e_v, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": alg / (kernel_ms * 1e-3) / 1e9 if kernel_ms else None, "peak": hbm,
+                     "unit": "GB/s", "frac": (alg / (kernel_ms * 1e-3) / 1e9 / hbm) if kernel_ms else None, "traffic": None,
+                     "peak_source": which, "kernel": "whole forward (all libsis3d launches of one step)",
+                     "kernel_ms_per_step": kernel_ms, "algorithmic_bytes_per_step": alg,
+                     "conv_ms_per_step": conv_ms, "top_kernels_ms": {k: round(v[0], 4) for k, v in top}},
+        "clocks": clocks.summary(),
+    }
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import port
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        ocfg, w = port.make_cfg("scannet"), weights()
+        data, views = case(1000)
+        t_all, n = [], 0
+        port.forward(ocfg, w, data, views)  # warm
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < args.cpu_baseline_seconds:
+            t1 = time.perf_counter()
+            port.forward(ocfg, w, data, views)
+            t_all.append(time.perf_counter() - t1)
+            n += 1
+        out["cpu_baseline"] = {"value": 1.0 / float(np.mean(t_all)), "unit": "scenes/s", "cores": cores, "kind": "port",
+                               "sample": f"{n} full cfg2 chunks in ~{args.cpu_baseline_seconds:.0f}s, torch-CPU fp32 oracle port"}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -65,7 +65,7 @@ int sis3d_roi_pool_levels(const float *feat1, const float *feat2, const float *f
  *
  * views: float[n_views][40] per view = world_to_camera(16) | grid_to_world(16) | bounds_min(3) |
  *        bounds_max(3) | pad(2)   (row-major 4x4; bounds already clamped to the volume)
- * depth: float[n_views][img_h][img_w];   intr = {fx, fy, cx, cy}
+ * depth: float[n_views][img_h][img_w];   fx, fy, cx, cy = pinhole intrinsics of the depth image
  * sis3d_project_map     : pix int16[n_views][Z*Y*X] = v*img_w+u of the pixel a voxel projects to or
  *                         -1; index = z*X*Y + y*X + x (the reference's linear index); counts
  *                         int32[n_views] = number of valid voxels per view (zeroed by the call).
@@ -78,7 +78,7 @@ int sis3d_roi_pool_levels(const float *feat1, const float *feat2, const float *f
  *                         `feats_t` (workspace of the same size).
  * ---------------------------------------------------------------------------------------------- */
 int sis3d_project_map(const float *views, const float *depth, int n_views, int img_w, int img_h,
-                      const float *intr, float depth_min, float depth_max, float voxel_size,
+                      float fx, float fy, float cx, float cy, float depth_min, float depth_max, float voxel_size,
                       int X, int Y, int Z, int16_t *pix, int32_t *counts, void *stream);
 int sis3d_project_compact(const int16_t *pix, int X, int Y, int Z, int64_t *lin3d, int64_t *lin2d,
                           void *workspace, size_t workspace_bytes, void *stream);
