@@ -1,0 +1,310 @@
+// conv_tc.cu -- 3x3x3 / stride-1 / pad-1 convolution as an implicit GEMM on the 5th-gen tensor cores.
+//
+//   D[128 voxels x BN] (TMEM, fp32)  +=  A[128 x 32] (smem, TF32)  x  B[BN x 32]^T (smem, TF32)
+//
+// * M tile = an 8x4x4 brick of output voxels.  For every filter tap (27) and every 32-channel slice of
+//   C_in, ONE 4-D TMA box {32 ch, 4 z, 4 y, 8 x} fetches the shifted input brick straight from the VC
+//   activation tensor; voxels outside the volume are zero-filled by the TMA unit, which *is* the
+//   convolution's zero padding -- no halo logic, no im2col buffer.  Rows land 128 B apart in the
+//   canonical K-major SWIZZLE_128B layout tcgen05.mma consumes.
+// * B tile = BN rows of the weight matrix W[C_out][27*C_in] (k = tap*C_in + c), 2-D TMA, same swizzle.
+// * Warp roles (128 threads): thread 0 = TMA producer, thread 32 = MMA issuer (tcgen05.mma
+//   kind::tf32, cta_group::1, M=128, N=BN, K=8 x4 per stage), all four warps = epilogue
+//   (tcgen05.ld 32x32b -> bias / residual / ReLU -> global).  4-stage full/empty mbarrier ring;
+//   tcgen05.commit releases smem slots and signals the accumulator.
+// * Tiles may be listed explicitly (ragged RoI crops packed on one zero-separated canvas, mask head)
+//   or implied by the volume.
+//
+// Reference call sites: Bottleneck.conv2 (lib/nets/backbones.py:21), geometry2.0 (:216),
+// rpn_net_level{1,2} (lib/nets/network.py:40,45), MaskBackbone.geometry.{2,4,6,8} (backbones.py:243-249).
+#include <cuda.h>
+#include "common.cuh"
+
+namespace sis3d {
+
+constexpr int TC_BX = 8, TC_BY = 4, TC_BZ = 4;
+constexpr int TC_BM = TC_BX * TC_BY * TC_BZ;  // 128
+constexpr int TC_KC = 32;                      // channels per stage: 32 * 4 B = 128 B = one swizzle row
+constexpr int TC_STAGES = 4;
+constexpr int TC_A_BYTES = TC_BM * 128;
+
+struct TcArgs {
+    const float *bias, *res;
+    float *out;
+    const int32_t *tiles;  // [n_tiles][8] = x0,y0,z0,x1,y1,z1,-,- (origin, exclusive valid end) or null
+    int X, Y, Z, cin, cout, act, out_ld, out_coff, res_ld, res_coff;
+    int tiles_y, tiles_z;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done, spins = 0;
+    do {
+        if (++spins > (1u << 28)) __trap();  // a broken pipeline becomes a CUDA error, never a hung GPU
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO=1 [16,30) | SBO=1024B>>4 [32,46) | version=1 [46,48) | layout=SWIZZLE_128B(2) [61,64)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                              const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+    constexpr int B_BYTES = BN * 128;
+    constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B needs 1024 B alignment
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + TC_STAGES * STAGE_BYTES);
+    uint64_t *empty = full + TC_STAGES;
+    uint64_t *acc_ready = empty + TC_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_ready + 1);
+
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        mbar_init(acc_ready, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {  // one full warp allocates BN TMEM columns (power of two >= 32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    // ---- which brick
+    int x0, y0, z0, x1, y1, z1;
+    if (a.tiles) {
+        const int32_t *t = a.tiles + (size_t)blockIdx.x * 8;
+        x0 = t[0]; y0 = t[1]; z0 = t[2]; x1 = t[3]; y1 = t[4]; z1 = t[5];
+    } else {
+        const int tz = blockIdx.x % a.tiles_z, ty = (blockIdx.x / a.tiles_z) % a.tiles_y, tx = blockIdx.x / (a.tiles_z * a.tiles_y);
+        x0 = tx * TC_BX; y0 = ty * TC_BY; z0 = tz * TC_BZ;
+        x1 = min(x0 + TC_BX, a.X); y1 = min(y0 + TC_BY, a.Y); z1 = min(z0 + TC_BZ, a.Z);
+    }
+    const int n0 = blockIdx.y * BN;
+    const int kchunks = a.cin / TC_KC;
+    const int total = 27 * kchunks;
+
+    if (threadIdx.x == 0) {
+        // ===== TMA producer =====
+        for (int it = 0; it < total; ++it) {
+            const int s = it % TC_STAGES;
+            const uint32_t ph = (it / TC_STAGES) & 1;
+            mbar_wait(empty + s, ph ^ 1);
+            mbar_expect_tx(full + s, STAGE_BYTES);
+            const int tap = it / kchunks, kc = it - tap * kchunks;
+            const int dx = tap / 9, dy = (tap / 3) % 3, dz = tap % 3;
+            uint8_t *sa = smem + s * STAGE_BYTES;
+            tma_load_4d(sa, &tmA, full + s, kc * TC_KC, z0 + dz - 1, y0 + dy - 1, x0 + dx - 1);
+            tma_load_2d(sa + TC_A_BYTES, &tmB, full + s, tap * a.cin + kc * TC_KC, n0);
+        }
+    } else if (threadIdx.x == 32) {
+        // ===== MMA issuer =====
+        // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
+        // A,B K-major, N>>3 at [17,23), M>>4 at [24,29)
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        for (int it = 0; it < total; ++it) {
+            const int s = it % TC_STAGES;
+            const uint32_t ph = (it / TC_STAGES) & 1;
+            mbar_wait(full + s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + TC_A_BYTES;
+#pragma unroll
+            for (int k = 0; k < TC_KC / 8; ++k)  // UMMA_K = 8 tf32 = 32 B: advance the start address inside the swizzle atom
+                umma_tf32(tmem_base, umma_desc(sa + k * 32), umma_desc(sb + k * 32), idesc, (it | k) ? 1u : 0u);
+            umma_commit(empty + s);  // frees the smem slot once these MMAs retire
+        }
+        umma_commit(acc_ready);
+    }
+    __syncwarp();
+
+    // ===== epilogue: TMEM lane r == output row r of the brick =====
+    mbar_wait(acc_ready, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int r = threadIdx.x;
+    const int vz = z0 + (r & 3), vy = y0 + ((r >> 2) & 3), vx = x0 + (r >> 4);
+    const bool valid = vx < x1 && vy < y1 && vz < z1;
+    const int64_t vox = ((int64_t)vx * a.Y + vy) * a.Z + vz;
+    float *orow = a.out + vox * a.out_ld + a.out_coff + n0;
+    const float *rrow = a.res ? a.res + vox * a.res_ld + a.res_coff + n0 : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (a.bias) {
+                    const float4 b = __ldg(reinterpret_cast<const float4 *>(a.bias + n0 + c * 32 + j));
+                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                }
+                if (rrow) {
+                    const float4 q = __ldg(reinterpret_cast<const float4 *>(rrow + c * 32 + j));
+                    o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+                }
+                if (a.act == 1) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                *reinterpret_cast<float4 *>(orow + c * 32 + j) = o;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+}
+
+// weights [cout][cin][3][3][3] -> [cout][27*cin] with k = tap*cin + c
+__global__ void pack_conv_weight_tc_kernel(const float *w, int cout, int cin, float *out) {
+    const int64_t total = (int64_t)cout * 27 * cin;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cin);
+        const int tap = (int)((i / cin) % 27);
+        const int n = (int)(i / ((int64_t)cin * 27));
+        out[i] = w[((int64_t)n * cin + c) * 27 + tap];
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {  // resolved through the runtime so libsis3d.so has no link-time dependency on libcuda
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+template <int BN>
+static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcArgs &a, int n_tiles, cudaStream_t s) {
+    const size_t smem = (size_t)TC_STAGES * (TC_A_BYTES + BN * 128) + 1024 + 256;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(conv3d_k3_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return SIS3D_ELAUNCH;
+        attr_done = true;
+    }
+    dim3 grid(n_tiles, a.cout / BN);
+    conv3d_k3_tc_kernel<BN><<<grid, 128, smem, s>>>(tmA, tmB, a);
+    return finish_launch();
+}
+
+}  // namespace sis3d
+using namespace sis3d;
+
+extern "C" int sis3d_pack_conv_weight_tc(const float *w, int cout, int cin, float *w_tc, void *stream) {
+    if (!w || !w_tc || cout <= 0 || cin <= 0) return SIS3D_EINVAL;
+    const int64_t total = (int64_t)cout * 27 * cin;
+    pack_conv_weight_tc_kernel<<<(int)imin64(cdiv64(total, 256), 148 * 8), 256, 0, (cudaStream_t)stream>>>(w, cout, cin, w_tc);
+    return finish_launch();
+}
+
+extern "C" int sis3d_conv3d_k3_tc_supported(int cin, int cout) {
+    return (cin % TC_KC == 0 && (cout == 32 || cout == 64 || cout % 128 == 0)) ? 1 : 0;
+}
+
+extern "C" int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const float *bias, const float *residual, int res_ld,
+                                  int res_coff, float *out, int out_ld, int out_coff, int X, int Y, int Z, int cin, int cout,
+                                  const int32_t *tiles, int n_tiles, int act, void *stream) {
+    if (!in || !w_tc || !out || X <= 0 || Y <= 0 || Z <= 0) return SIS3D_EINVAL;
+    if (!sis3d_conv3d_k3_tc_supported(cin, cout)) return SIS3D_EUNSUPPORTED;
+    if (((uintptr_t)in | (uintptr_t)w_tc | (uintptr_t)out) & 15) return SIS3D_EINVAL;
+    if ((out_ld | out_coff | res_ld | res_coff) & 3) return SIS3D_EINVAL;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return SIS3D_EUNSUPPORTED;
+    const int BN = cout >= 128 ? 128 : cout;
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X};
+        cuuint64_t strides[3] = {(cuuint64_t)cin * 4, (cuuint64_t)Z * cin * 4, (cuuint64_t)Y * Z * cin * 4};
+        cuuint32_t box[4] = {TC_KC, TC_BZ, TC_BY, TC_BX};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return SIS3D_EINVAL;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)27 * cin, (cuuint64_t)cout};
+        cuuint64_t strides[1] = {(cuuint64_t)27 * cin * 4};
+        cuuint32_t box[2] = {TC_KC, (cuuint32_t)BN};
+        cuuint32_t estr[2] = {1, 1};
+        if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)w_tc, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return SIS3D_EINVAL;
+    }
+    TcArgs a;
+    a.bias = bias; a.res = residual; a.out = out; a.tiles = tiles;
+    a.X = X; a.Y = Y; a.Z = Z; a.cin = cin; a.cout = cout; a.act = act;
+    a.out_ld = out_ld; a.out_coff = out_coff; a.res_ld = res_ld; a.res_coff = res_coff;
+    a.tiles_y = cdiv(Y, TC_BY); a.tiles_z = cdiv(Z, TC_BZ);
+    if (!tiles) n_tiles = cdiv(X, TC_BX) * a.tiles_y * a.tiles_z;
+    if (n_tiles <= 0) return SIS3D_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (BN) {
+        case 32: return launch_tc<32>(tmA, tmB, a, n_tiles, s);
+        case 64: return launch_tc<64>(tmA, tmB, a, n_tiles, s);
+        default: return launch_tc<128>(tmA, tmB, a, n_tiles, s);
+    }
+}

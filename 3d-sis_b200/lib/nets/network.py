@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -64,6 +65,9 @@ class Network(nn.Module):
         self._region_cache = {}
         self._const_cache = {}
         self._keep_debug = False
+        self._packed_tc = {}
+        # conv math for the 3x3x3 layers: 'tf32' = tcgen05 tensor cores (default), 'fp32' = CUDA-core exact path
+        self._math = os.environ.get("SIS3D_CONV_MATH", str(cfg.get("CONV_MATH", "tf32"))).lower()
         self._prof = None  # name -> [(start_event, end_event)] when per-kernel timing is on (bench.py)
 
     # ------------------------------------------------------------------ parameters
@@ -125,7 +129,7 @@ class Network(nn.Module):
         v = self._version()
         if v == self._packed_version:
             return
-        self._packed = {}
+        self._packed, self._packed_tc = {}, {}
         params = dict(self.named_parameters())
         for name, p in params.items():
             if not name.endswith(".weight"):
@@ -140,6 +144,10 @@ class Network(nn.Module):
             S.check(S.lib.sis3d_pack_conv_weight(S.ptr(w), cout, cin, ks, S.ptr(packed), S.stream()), "pack")
             b = params.get(base + ".bias")
             self._packed[base] = (packed, None if b is None else b.detach().float().contiguous(), cout, cin, ks)
+            if ks == 3 and S.lib.sis3d_conv3d_k3_tc_supported(cin, cout):
+                wtc = torch.empty(cout, 27 * cin, dtype=torch.float32, device=w.device)
+                S.check(S.lib.sis3d_pack_conv_weight_tc(S.ptr(w), cout, cin, S.ptr(wtc), S.stream()), "pack_tc")
+                self._packed_tc[base] = wtc
         torch.cuda.current_stream().synchronize()
         self._packed_version = v
 
@@ -178,12 +186,24 @@ class Network(nn.Module):
             pad = 1 if ks == 3 else 0
         if out_dims is None:
             out_dims = tuple(d // 2 for d in x.dims) if stride == 2 else x.dims
+        regions_given = regions
         if regions is None:
             regions, n_tiles = self._regions_single(x, out_dims, stride)
         else:
             regions, n_tiles = regions
         if out is None:
             out = Act(torch.empty(*out_dims, cout, dtype=torch.float32, device=x.t.device), out_dims, cout)
+        if (self._math == "tf32" and regions_given is None and name in self._packed_tc and stride == 1 and pad == 1
+                and x.layout == "vc" and x.ld == x.C and x.coff == 0 and act in (0, 1)):
+            tok = self._rec(f"conv_tc[{name}]")
+            S.check(S.lib.sis3d_conv3d_k3_tc(S.ptr(x.t), S.ptr(self._packed_tc[name]), S.ptr(bias),
+                                             S.ptr(residual.t) if residual is not None else None,
+                                             residual.ld if residual is not None else 0,
+                                             residual.coff if residual is not None else 0,
+                                             S.ptr(out.t), out.ld, out.coff, *x.dims, cin, cout, None, 0, act, S.stream()),
+                    f"conv3d_k3_tc[{name}]")
+            self._rec_end(tok)
+            return out
         in_sc = 1 if x.layout == "vc" else x.nvox
         xin = x.t if x.coff == 0 else x.t.reshape(-1)[x.coff:]
         tok = self._rec(f"conv[{name}]")

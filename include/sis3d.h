@@ -120,6 +120,21 @@ int sis3d_conv3d(const float *in, int64_t in_chan_stride, const float *w_packed,
                  const float *residual, int res_ld, int res_coff, float *out, int out_ld, int out_coff,
                  const sis3d_region *regions, int n_regions, int n_tiles, int cin, int cout, int ks,
                  int stride, int pad, int act, void *stream);
+/* ------------------------------------------------------------------------------------------------
+ * Tensor-core path for the 3x3x3 / stride 1 / pad 1 layers (same call sites as sis3d_conv3d):
+ * tcgen05.mma kind::tf32 with fp32 accumulation in TMEM, operands staged by 4-D/2-D TMA boxes
+ * (csrc/conv_tc.cu).  `in` is a dense VC tensor [X][Y][Z][cin]; w_tc comes from
+ * sis3d_pack_conv_weight_tc ([cout][27*cin]).  tiles == NULL covers the whole volume with 8x4x4
+ * bricks; otherwise tiles int32[n_tiles][8] = {x0,y0,z0,x1,y1,z1,0,0} lists brick origins and the
+ * exclusive end of the voxels to be written (ragged RoI crops packed on one canvas).
+ * Requires cin % 32 == 0 and cout in {32, 64, 128k}; returns SIS3D_EUNSUPPORTED otherwise.
+ * ---------------------------------------------------------------------------------------------- */
+int sis3d_pack_conv_weight_tc(const float *w_oidhw, int cout, int cin, float *w_tc, void *stream);
+int sis3d_conv3d_k3_tc_supported(int cin, int cout);
+int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const float *bias, const float *residual,
+                       int res_ld, int res_coff, float *out, int out_ld, int out_coff, int X, int Y,
+                       int Z, int cin, int cout, const int32_t *tiles, int n_tiles, int act, void *stream);
+
 /* MaxPool3d(3,1,1) on a VC tensor (lib/nets/backbones.py:207,212,220); output row stride out_ld and
  * channel offset out_coff as for the convolution. */
 int sis3d_maxpool3(const float *in, float *out, int out_ld, int out_coff, int X, int Y, int Z, int C, void *stream);
