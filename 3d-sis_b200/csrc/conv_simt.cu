@@ -26,6 +26,9 @@ struct ConvArgs {
     int out_ld, out_coff, res_ld, res_coff;
     int64_t in_sc;
     int fast;  // in_sc == 1 && cin % 16 == 0
+    int dense_m;          // > 0: no region table, input is a dense [dense_m][cin] matrix (linear layer)
+    int k_per_split;      // > 0: split-K, blockIdx.z owns K range [z*k_per_split, ...), raw partials to out + z*split_stride
+    int64_t split_stride;
 };
 
 template <int BN, int TM>
@@ -39,7 +42,7 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_f32(const ConvArgs 
     const int t = threadIdx.x;
     const int tile = blockIdx.x;
     const int n0 = blockIdx.y * BN;
-    if (t == 0) {
+    if (t == 0 && !a.dense_m) {
         int lo = 0, hi = a.n_regions - 1;
         while (lo < hi) {
             int mid = (lo + hi + 1) >> 1;
@@ -48,7 +51,16 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_f32(const ConvArgs 
         s_region = lo;
     }
     __syncthreads();
-    const sis3d_region R = a.regions[s_region];
+    sis3d_region R;
+    if (a.dense_m) {
+        R.in_off = R.out_off = R.res_off = 0;
+        R.in_dim[0] = R.out_dim[0] = a.dense_m; R.in_dim[1] = R.in_dim[2] = R.out_dim[1] = R.out_dim[2] = 1;
+        R.in_stride[0] = R.in_stride[1] = R.in_stride[2] = a.cin;
+        R.out_stride[0] = R.out_stride[1] = R.out_stride[2] = 0;
+        R.tile_begin = 0;
+    } else {
+        R = a.regions[s_region];
+    }
     const int oyz = R.out_dim[1] * R.out_dim[2];
     const int m_total = R.out_dim[0] * oyz;
     const int m_base = (tile - R.tile_begin) * BM;
@@ -78,7 +90,9 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_f32(const ConvArgs 
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
     const int ks2 = a.ks * a.ks;
-    for (int k0 = 0; k0 < a.K; k0 += BK) {
+    const int k_begin = a.k_per_split ? blockIdx.z * a.k_per_split : 0;
+    const int k_end = a.k_per_split ? min(a.K, k_begin + a.k_per_split) : a.K;
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
         // ---------------- gather A
         float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
         if (a.fast) {
@@ -145,7 +159,21 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_f32(const ConvArgs 
     for (int i = 0; i < TM; ++i) {
         const int m = m_base + ty * TM + i;
         if (m >= m_total) continue;
-        float *orow = a.out + R.out_off + (int64_t)m * a.out_ld + a.out_coff;
+        int64_t ooff = (int64_t)m * a.out_ld;
+        if (R.out_stride[0] | R.out_stride[1] | R.out_stride[2]) {
+            const int ox = m / oyz, orem = m - ox * oyz, oy = orem / R.out_dim[2], oz = orem - oy * R.out_dim[2];
+            ooff = ox * R.out_stride[0] + oy * R.out_stride[1] + oz * R.out_stride[2];
+        }
+        float *orow = a.out + R.out_off + ooff + a.out_coff;
+        if (a.k_per_split) {  // raw partial sums; bias/activation applied by splitk_reduce_kernel
+            orow = a.out + (int64_t)blockIdx.z * a.split_stride + (int64_t)m * a.out_ld;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const int n = n0 + tx * TN + j;
+                if (n < a.cout) orow[n] = acc[i][j];
+            }
+            continue;
+        }
         const float *rrow = a.res ? a.res + R.res_off + (int64_t)m * a.res_ld + a.res_coff : nullptr;
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
@@ -159,6 +187,17 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_f32(const ConvArgs 
             orow[n] = v;
         }
     }
+}
+
+__global__ void splitk_reduce_kernel(const float *part, int splits, int64_t split_stride, const float *bias, float *y, int M,
+                                     int N, int act) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * N) return;
+    float v = 0.f;
+    for (int s = 0; s < splits; ++s) v += part[(int64_t)s * split_stride + i];  // fixed order -> deterministic
+    if (bias) v += bias[i % N];
+    if (act == 1) v = fmaxf(v, 0.f);
+    y[i] = v;
 }
 
 // weights [cout][cin][ks][ks][ks] -> [K = tap*cin + c][ldw], zero padded columns
@@ -243,6 +282,7 @@ extern "C" int sis3d_conv3d(const float *in, int64_t in_chan_stride, const float
     a.pad = pad; a.act = act; a.K = ks * ks * ks * cin; a.out_ld = out_ld; a.out_coff = out_coff;
     a.res_ld = res_ld; a.res_coff = res_coff; a.in_sc = in_chan_stride;
     a.fast = (in_chan_stride == 1 && cin % 16 == 0 && ((uintptr_t)in % 16 == 0)) ? 1 : 0;
+    a.dense_m = 0; a.k_per_split = 0; a.split_stride = 0;
     cudaStream_t s = (cudaStream_t)stream;
     if (cout <= 32) {
         dim3 grid(n_tiles, cdiv(cout, 32));
@@ -250,6 +290,42 @@ extern "C" int sis3d_conv3d(const float *in, int64_t in_chan_stride, const float
     } else {
         dim3 grid(n_tiles, cdiv(cout, 64));
         conv3d_igemm_f32<64, 4><<<grid, kConvThreads, 0, s>>>(a);
+    }
+    return finish_launch();
+}
+
+static int linear_splits(int M, int N, int K) {
+    const int tiles = cdiv(M, BM) * cdiv(N, 64);
+    int splits = max(1, min(K / 64, (2 * kNumSMs + tiles - 1) / tiles));
+    return splits;
+}
+extern "C" size_t sis3d_linear_workspace_bytes(int M, int N, int K) {
+    return sizeof(float) * (size_t)linear_splits(M, N, K) * M * N + 16;
+}
+extern "C" int sis3d_linear(const float *x, const float *w_packed, const float *bias, float *y, int M, int K, int N, int act,
+                            void *workspace, size_t workspace_bytes, void *stream) {
+    if (!x || !w_packed || !y || M <= 0 || K <= 0 || N <= 0 || K % 16 != 0 || ((uintptr_t)x & 15)) return SIS3D_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    int splits = linear_splits(M, N, K);
+    ConvArgs a;
+    a.in = x; a.w = w_packed; a.bias = bias; a.res = nullptr; a.out = y; a.regions = nullptr; a.n_regions = 0;
+    a.cin = K; a.cout = N; a.ldw = (N + 3) & ~3; a.ks = 1; a.stride = 1; a.pad = 0; a.act = act; a.K = K;
+    a.out_ld = N; a.out_coff = 0; a.res_ld = 0; a.res_coff = 0; a.in_sc = 1; a.fast = 1; a.dense_m = M;
+    a.k_per_split = 0; a.split_stride = 0;
+    if (splits > 1) {
+        if (!workspace || workspace_bytes < sizeof(float) * (size_t)splits * M * N) return SIS3D_EWORKSPACE;
+        a.k_per_split = cdiv(cdiv(K, splits), BK) * BK;
+        splits = cdiv(K, a.k_per_split);
+        a.split_stride = (int64_t)M * N;
+        a.out = (float *)workspace;
+        a.bias = nullptr; a.act = 0;
+    }
+    dim3 grid(cdiv(M, BM), cdiv(N, N <= 32 ? 32 : 64), splits > 1 ? splits : 1);
+    if (N <= 32) conv3d_igemm_f32<32, 2><<<grid, kConvThreads, 0, s>>>(a);
+    else conv3d_igemm_f32<64, 4><<<grid, kConvThreads, 0, s>>>(a);
+    if (splits > 1) {
+        splitk_reduce_kernel<<<cdiv(M * N, 256), 256, 0, s>>>((const float *)workspace, splits, a.split_stride, bias, y, M, N, act);
+        return finish_launch(2);
     }
     return finish_launch();
 }

@@ -29,7 +29,7 @@ class Region(C.Structure):
     """struct sis3d_region (include/sis3d.h)."""
     _fields_ = [("in_off", C.c_int64), ("out_off", C.c_int64), ("res_off", C.c_int64),
                 ("in_dim", C.c_int32 * 3), ("out_dim", C.c_int32 * 3), ("in_stride", C.c_int64 * 3),
-                ("tile_begin", C.c_int32), ("pad_", C.c_int32)]
+                ("out_stride", C.c_int64 * 3), ("tile_begin", C.c_int32), ("pad_", C.c_int32)]
 
 
 class RpnLevel(C.Structure):
@@ -46,13 +46,14 @@ SYMBOLS = ["sis3d_strerror", "sis3d_version", "sis3d_launch_count", "sis3d_nms_w
            "sis3d_roi_pool_fwd", "sis3d_roi_pool_levels", "sis3d_project_map", "sis3d_project_compact",
            "sis3d_project_compact_workspace_bytes", "sis3d_backproject_pairs", "sis3d_project_scatter_lists",
            "sis3d_backproject_max", "sis3d_pack_conv_weight", "sis3d_conv3d", "sis3d_maxpool3",
-           "sis3d_vc_to_ncdhw", "sis3d_pack_conv_weight_tc", "sis3d_conv3d_k3_tc_supported", "sis3d_conv3d_k3_tc",
+           "sis3d_vc_to_ncdhw", "sis3d_linear_workspace_bytes", "sis3d_linear", "sis3d_pack_conv_weight_tc", "sis3d_conv3d_k3_tc_supported", "sis3d_conv3d_k3_tc",
            "sis3d_rpn_workspace_bytes", "sis3d_rpn_proposals", "sis3d_detect_decode"]
 
 lib.sis3d_strerror.restype = C.c_char_p
 lib.sis3d_launch_count.restype = C.c_int64
 lib.sis3d_nms_workspace_bytes.restype = C.c_size_t
 lib.sis3d_rpn_workspace_bytes.restype = C.c_size_t
+lib.sis3d_linear_workspace_bytes.restype = C.c_size_t
 lib.sis3d_project_compact_workspace_bytes.restype = C.c_size_t
 
 
@@ -91,6 +92,7 @@ def make_regions(entries, device):
         r.in_off, r.out_off, r.res_off = int(e["in_off"]), int(e["out_off"]), int(e.get("res_off", 0))
         for k in range(3):
             r.in_dim[k], r.out_dim[k], r.in_stride[k] = int(e["in_dim"][k]), int(e["out_dim"][k]), int(e["in_stride"][k])
+            r.out_stride[k] = int(e["out_stride"][k]) if "out_stride" in e else 0
         r.tile_begin = tiles
         m = int(e["out_dim"][0]) * int(e["out_dim"][1]) * int(e["out_dim"][2])
         tiles += (m + TILE_M - 1) // TILE_M

@@ -26,30 +26,36 @@ def _corner_rays(intrinsic, image_dims, depth_min, depth_max):
     return pts
 
 
+_CORNER_CACHE = {}
+
+
 def view_params(intrinsic, image_dims, depth_min, depth_max, volume_dims, depths, poses, world2grid):
     """Pack the per-view constants consumed by sis3d_project_map: float32 [n,40] (CPU tensor).
 
-    world_to_camera | grid_to_world | clamped frustum bounds (projection.py:56-60, 39-49)."""
+    world_to_camera | grid_to_world | clamped frustum bounds (projection.py:56-60, 39-49), computed for
+    all views in one batch of fp32 torch-CPU ops (bit-identical to the reference's per-view loop)."""
     poses = torch.as_tensor(poses, dtype=torch.float32).reshape(-1, 4, 4).cpu()
     n = poses.shape[0]
-    w2g = torch.as_tensor(world2grid, dtype=torch.float32).cpu()
-    w2g = w2g.reshape(-1, 4, 4)
+    w2g = torch.as_tensor(world2grid, dtype=torch.float32).cpu().reshape(-1, 4, 4)
     if w2g.shape[0] == 1:
-        w2g = w2g.expand(n, 4, 4)
-    corners = _corner_rays(intrinsic, image_dims, depth_min, depth_max)
-    dims = torch.tensor([float(v) for v in volume_dims], dtype=torch.float32)
+        w2g = w2g.expand(n, 4, 4).contiguous()
+    key = (float(intrinsic[0][0]), float(intrinsic[1][1]), float(intrinsic[0][2]), float(intrinsic[1][2]),
+           int(image_dims[0]), int(image_dims[1]), float(depth_min), float(depth_max))
+    corners = _CORNER_CACHE.get(key)
+    if corners is None:
+        corners = _CORNER_CACHE[key] = _corner_rays(intrinsic, image_dims, depth_min, depth_max)
     out = torch.zeros(n, 40, dtype=torch.float32)
-    for i in range(n):
-        c2w, g = poses[i], w2g[i]
-        out[i, 0:16] = torch.inverse(c2w).reshape(-1)
-        out[i, 16:32] = torch.inverse(g).reshape(-1)
-        p = torch.bmm(c2w.repeat(8, 1, 1), corners)
-        pl = torch.round(torch.bmm(g.repeat(8, 1, 1), torch.floor(p)))[:, :3, 0]
-        pu = torch.round(torch.bmm(g.repeat(8, 1, 1), torch.ceil(p)))[:, :3, 0]
-        lo = torch.minimum(pl.min(0)[0], pu.min(0)[0])
-        hi = torch.maximum(pl.max(0)[0], pu.max(0)[0])
-        out[i, 32:35] = torch.clamp(lo, min=0)
-        out[i, 35:38] = torch.minimum(hi, dims)
+    out[:, 0:16] = torch.inverse(poses).reshape(n, 16)
+    out[:, 16:32] = torch.inverse(w2g).reshape(n, 16)
+    c2w8 = poses[:, None].expand(n, 8, 4, 4).reshape(n * 8, 4, 4)
+    g8 = w2g[:, None].expand(n, 8, 4, 4).reshape(n * 8, 4, 4)
+    p = torch.bmm(c2w8, corners.repeat(n, 1, 1))
+    pl = torch.round(torch.bmm(g8, torch.floor(p)))[:, :3, 0].reshape(n, 8, 3)
+    pu = torch.round(torch.bmm(g8, torch.ceil(p)))[:, :3, 0].reshape(n, 8, 3)
+    lo = torch.minimum(pl.min(1)[0], pu.min(1)[0])
+    hi = torch.maximum(pl.max(1)[0], pu.max(1)[0])
+    out[:, 32:35] = torch.clamp(lo, min=0)
+    out[:, 35:38] = torch.minimum(hi, torch.tensor([float(v) for v in volume_dims], dtype=torch.float32))
     return out
 
 

@@ -68,6 +68,8 @@ class Network(nn.Module):
         self._packed_tc = {}
         # conv math for the 3x3x3 layers: 'tf32' = tcgen05 tensor cores (default), 'fp32' = CUDA-core exact path
         self._math = os.environ.get("SIS3D_CONV_MATH", str(cfg.get("CONV_MATH", "tf32"))).lower()
+        self._graphs = {}
+        self._use_graph = os.environ.get("SIS3D_CUDA_GRAPH", "1") != "0"
         self._prof = None  # name -> [(start_event, end_event)] when per-kernel timing is on (bench.py)
 
     # ------------------------------------------------------------------ parameters
@@ -216,6 +218,19 @@ class Network(nn.Module):
         self._rec_end(tok)
         return out
 
+    def _linear(self, x, name, act):
+        """y = act(x W^T + b) through the split-K kernel (classifier MLP + heads)."""
+        packed, bias, cout, cin, _ = self._packed[name]
+        M = x.shape[0]
+        y = torch.empty(M, cout, dtype=torch.float32, device=x.device)
+        nbytes = int(S.lib.sis3d_linear_workspace_bytes(M, cout, cin))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        tok = self._rec(f"linear[{name}]")
+        S.check(S.lib.sis3d_linear(S.ptr(x), S.ptr(packed), S.ptr(bias), S.ptr(y), M, cin, cout, act, S.ptr(ws),
+                                   C.c_size_t(nbytes), S.stream()), f"linear[{name}]")
+        self._rec_end(tok)
+        return y
+
     def _bottleneck(self, x: Act, name, out: Act = None):
         """1x1 -> relu -> 3x3x3 -> relu -> 1x1 (+x) -> relu  (reference: backbones.py:28-40)."""
         y = self._conv(x, name + ".conv1", act=1)
@@ -255,21 +270,23 @@ class Network(nn.Module):
             self._const_cache[key] = v
         return v
 
-    def _backproject(self, blobs, killing_inds, dims, dev):
+    def _backproject(self, blobs, killing_inds, dims, dev, fused=None):
         """Views -> VC feature volume (reference: trainval.py:797-820 + network.py:194-239)."""
-        imgs = blobs["nearest_images"]
-        feats = imgs["images"][0]
-        if not cfg.USE_IMAGES_GT:
-            if getattr(self, "image_enet_fixed", None) is None:
-                raise S.Sis3dError("USE_IMAGES_GT=False needs the 2D ENet encoder (upstream of the hot path, "
-                                   "SURVEY 8f2): attach torch modules as net.image_enet_fixed/_trainable or feed "
-                                   "ENet-shaped features with USE_IMAGES_GT=True")
-            with torch.no_grad():
-                feats = self.image_enet_trainable(self.image_enet_fixed(feats.to(dev)))
-        feats = feats.to(dev, torch.float32, non_blocking=True)
-        n = feats.shape[0]
         w, h = int(cfg.DEPTH_SHAPE[0]), int(cfg.DEPTH_SHAPE[1])
-        if "proj_ind_3d" in blobs:
+        if fused is not None:
+            feats = fused["feats"]
+        else:
+            feats = blobs["nearest_images"]["images"][0]
+            if not cfg.USE_IMAGES_GT:
+                if getattr(self, "image_enet_fixed", None) is None:
+                    raise S.Sis3dError("USE_IMAGES_GT=False needs the 2D ENet encoder (upstream of the hot path, "
+                                       "SURVEY 8f2): attach torch modules as net.image_enet_fixed/_trainable or feed "
+                                       "ENet-shaped features with USE_IMAGES_GT=True")
+                with torch.no_grad():
+                    feats = self.image_enet_trainable(self.image_enet_fixed(feats.to(dev)))
+            feats = feats.to(dev, torch.float32, non_blocking=True)
+        n = feats.shape[0]
+        if fused is None:
             # reference calling convention: precomputed, stacked index lists + killing_inds
             l3 = blobs["proj_ind_3d"][0].to(dev).contiguous()
             l2 = blobs["proj_ind_2d"][0].to(dev).contiguous()
@@ -285,9 +302,7 @@ class Network(nn.Module):
             self._proj_counts = None
         else:
             # fused path: depth/pose/world2grid in, no index lists ever materialised
-            vp = proj.view_params(cfg.INTRINSIC, (w, h), cfg.PROJ_DEPTH_MIN, cfg.PROJ_DEPTH_MAX, dims,
-                                  None, imgs["poses"][0], imgs["world2grid"][0]).to(dev, non_blocking=True)
-            depths = torch.as_tensor(imgs["depths"][0]).to(dev, torch.float32, non_blocking=True).contiguous()
+            vp, depths = fused["vp"], fused["depths"]
             intr = (cfg.INTRINSIC[0][0], cfg.INTRINSIC[1][1], cfg.INTRINSIC[0][2], cfg.INTRINSIC[1][2])
             tok = self._rec("project_map")
             pix, counts = proj.project_maps(vp, depths, intr, (cfg.PROJ_DEPTH_MIN, cfg.PROJ_DEPTH_MAX, cfg.VOXEL_SIZE),
@@ -359,18 +374,21 @@ class Network(nn.Module):
                                             S.f32(1.0 / self._feat_stride[0]), R, *f1.dims, f1.C, P, P, P, S.ptr(rois),
                                             S.ptr(pool5), None, S.stream()), "roi_pool_levels")
         self._rec_end(tok)
-        x = Act(pool5, (R, 1, 1), pool5.shape[1])
-        for i in (0, 2, 4):
-            x = self._conv(x, f"classifier.{i}", act=1)
-        cls_score = self._conv(x, "classifier_cls_score_net")
-        bbox_pred = self._conv(x, "classifier_bbox_pred_net")
+        x = pool5
+        for name, act in (("classifier.0", 1), ("classifier.2", 1), ("classifier.4", 1)):
+            x = self._linear(x, name, act)
+        cls_score = Act(self._linear(x, "classifier_cls_score_net", 0), (R, 1, 1), int(cfg.NUM_CLASSES))
+        bbox_pred = Act(self._linear(x, "classifier_bbox_pred_net", 0), (R, 1, 1), int(cfg.NUM_CLASSES) * 6)
         if self._keep_debug:
             self._predictions["pool5"] = pool5
         return cls_score.t.view(R, -1), bbox_pred.t.view(R, -1)
 
     def _mask_branch(self, scene_ncdhw, det_host, n):
-        """Ragged per-RoI mask head (reference: network.py:283-317): all kept crops go through each of
-        the six layers in ONE launch per layer via a region table."""
+        """Ragged per-RoI mask head (reference: network.py:283-317).  All kept crops are packed along x on
+        one zero-initialised canvas [sum(w_j + 1), max h, max l, 64] (one zero slab between crops = the
+        crop-border zero padding), so each of the six layers is ONE launch: layer 1 (C_in = 2, windowed
+        NCDHW scene) and the 1x1 head on the fp32 CUDA-core kernel, the four 64->64 3x3x3 layers on the
+        tcgen05 kernel driven by an explicit list of 8x4x4 bricks."""
         keep = [i for i in range(n) if det_host[i, 8] > 0.5]
         if not keep:
             return []
@@ -381,22 +399,53 @@ class Network(nn.Module):
         vox = [s[0] * s[1] * s[2] for s in sizes]
         offs = np.concatenate([[0], np.cumsum(vox)]).astype(np.int64)
         total = int(offs[-1])
-        mb = self.mask_backbone
-        bufs = [torch.empty(total * 64, dtype=torch.float32, device=dev) for _ in range(2)]
         ncls = self._packed["mask_backbone.geometry.10"][2]
         outb = torch.empty(total * ncls, dtype=torch.float32, device=dev)
-        first = S.make_regions([dict(in_off=(c[0] * Y + c[1]) * Z + c[2], out_off=int(offs[j]) * 64, in_dim=s, out_dim=s,
-                                     in_stride=(Y * Z, Z, 1)) for j, (c, s) in enumerate(zip(crops, sizes))], dev)
-        mid = S.make_regions([dict(in_off=int(offs[j]) * 64, out_off=int(offs[j]) * 64, in_dim=s, out_dim=s,
-                                   in_stride=(s[1] * s[2] * 64, s[2] * 64, 64)) for j, s in enumerate(sizes)], dev)
-        last = S.make_regions([dict(in_off=int(offs[j]) * 64, out_off=int(offs[j]) * ncls, in_dim=s, out_dim=s,
-                                    in_stride=(s[1] * s[2] * 64, s[2] * 64, 64)) for j, s in enumerate(sizes)], dev)
         scene = Act(scene_ncdhw, (X, Y, Z), 2, layout="ncdhw")
-        x = self._conv(scene, "mask_backbone.geometry.0", act=1, regions=first, out_dims=(total, 1, 1),
-                       out=Act(bufs[0], (total, 1, 1), 64))
-        for li, idx in enumerate((2, 4, 6, 8)):
-            x = self._conv(x, f"mask_backbone.geometry.{idx}", act=1, regions=mid, out_dims=(total, 1, 1),
-                           out=Act(bufs[(li + 1) % 2], (total, 1, 1), 64))
+        use_tc = self._math == "tf32" and "mask_backbone.geometry.2" in self._packed_tc
+        if use_tc:
+            Yc, Zc = max(s[1] for s in sizes), max(s[2] for s in sizes)
+            xoff = np.concatenate([[0], np.cumsum([s[0] + 1 for s in sizes])]).astype(np.int64)
+            Xc = int(xoff[-1])
+            cs = (Yc * Zc * 64, Zc * 64, 64)  # canvas voxel strides
+            bufs = [torch.zeros(Xc, Yc, Zc, 64, dtype=torch.float32, device=dev) for _ in range(2)]
+            first = S.make_regions([dict(in_off=(c[0] * Y + c[1]) * Z + c[2], out_off=int(xoff[j]) * cs[0], in_dim=s,
+                                         out_dim=s, in_stride=(Y * Z, Z, 1), out_stride=cs)
+                                    for j, (c, s) in enumerate(zip(crops, sizes))], dev)
+            last = S.make_regions([dict(in_off=int(xoff[j]) * cs[0], out_off=int(offs[j]) * ncls, in_dim=s, out_dim=s,
+                                        in_stride=cs) for j, s in enumerate(sizes)], dev)
+            tiles = []
+            for j, s in enumerate(sizes):
+                x0 = int(xoff[j])
+                for bx in range(0, s[0], 8):
+                    for by in range(0, s[1], 4):
+                        for bz in range(0, s[2], 4):
+                            tiles.append((x0 + bx, by, bz, x0 + s[0], s[1], s[2], 0, 0))
+            tiles_t = torch.tensor(tiles, dtype=torch.int32).to(dev, non_blocking=True)
+            x = self._conv(scene, "mask_backbone.geometry.0", act=1, regions=first, out_dims=(Xc, Yc, Zc),
+                           out=Act(bufs[0], (Xc, Yc, Zc), 64))
+            for li, idx in enumerate((2, 4, 6, 8)):
+                name = f"mask_backbone.geometry.{idx}"
+                dst = Act(bufs[(li + 1) % 2], (Xc, Yc, Zc), 64)
+                tok = self._rec(f"conv_tc[{name}]")
+                S.check(S.lib.sis3d_conv3d_k3_tc(S.ptr(x.t), S.ptr(self._packed_tc[name]), None, None, 0, 0, S.ptr(dst.t), 64,
+                                                 0, Xc, Yc, Zc, 64, 64, S.ptr(tiles_t), len(tiles), 1, S.stream()),
+                        f"conv3d_k3_tc[{name}]")
+                self._rec_end(tok)
+                x = dst
+        else:
+            bufs = [torch.empty(total * 64, dtype=torch.float32, device=dev) for _ in range(2)]
+            first = S.make_regions([dict(in_off=(c[0] * Y + c[1]) * Z + c[2], out_off=int(offs[j]) * 64, in_dim=s,
+                                         out_dim=s, in_stride=(Y * Z, Z, 1)) for j, (c, s) in enumerate(zip(crops, sizes))], dev)
+            mid = S.make_regions([dict(in_off=int(offs[j]) * 64, out_off=int(offs[j]) * 64, in_dim=s, out_dim=s,
+                                       in_stride=(s[1] * s[2] * 64, s[2] * 64, 64)) for j, s in enumerate(sizes)], dev)
+            last = S.make_regions([dict(in_off=int(offs[j]) * 64, out_off=int(offs[j]) * ncls, in_dim=s, out_dim=s,
+                                        in_stride=(s[1] * s[2] * 64, s[2] * 64, 64)) for j, s in enumerate(sizes)], dev)
+            x = self._conv(scene, "mask_backbone.geometry.0", act=1, regions=first, out_dims=(total, 1, 1),
+                           out=Act(bufs[0], (total, 1, 1), 64))
+            for li, idx in enumerate((2, 4, 6, 8)):
+                x = self._conv(x, f"mask_backbone.geometry.{idx}", act=1, regions=mid, out_dims=(total, 1, 1),
+                               out=Act(bufs[(li + 1) % 2], (total, 1, 1), 64))
         y = self._conv(x, "mask_backbone.geometry.10", pad=0, act=2, regions=last, out_dims=(total, 1, 1),
                        out=Act(outb, (total, 1, 1), ncls))
         masks = []
@@ -406,9 +455,56 @@ class Network(nn.Module):
         return masks
 
     # ------------------------------------------------------------------ forward
+    def _static_stage(self, scene_t, dims, blobs=None, killing_inds=None, fused=None):
+        """Every fixed-shape step: back-projection -> backbone -> RPN/NMS -> RoI pool -> classifier ->
+        detection decode.  No host synchronisation inside, so the whole stage can be replayed as one CUDA
+        graph per (scene shape, #views)."""
+        dev = scene_t.device
+        P = self._predictions
+        scene = Act(scene_t, dims, 2, layout="ncdhw")
+        imageft = None
+        if cfg.USE_IMAGES:
+            imageft = self._backproject(blobs, killing_inds, dims, dev, fused)
+            self._imageft_vc = imageft.t if self._keep_debug else None
+        level1, level2 = self._backbone(scene, imageft)
+        if self._keep_debug:
+            P["level1_vc"], P["level2_vc"] = level1.t, level2.t
+        rois, scores, level_ids, num = self._region_proposal((level1, level2, None), dims)
+        out = dict(rois=rois, scores=scores, level_ids=level_ids, num=num)
+        if cfg.USE_CLASS:
+            cls_score, bbox_pred = self._classify((level1, level2, None), rois, level_ids)
+            R, nc = rois.shape[0], int(cfg.NUM_CLASSES)
+            cls_prob = torch.empty(R, nc, dtype=torch.float32, device=dev)
+            cls_pred = torch.empty(R, dtype=torch.int64, device=dev)
+            det = torch.empty(R, 16, dtype=torch.float32, device=dev)
+            tok = self._rec("detect_decode")
+            S.check(S.lib.sis3d_detect_decode(S.ptr(rois), S.ptr(num), R, S.ptr(cls_score), S.ptr(bbox_pred), nc,
+                                              *dims, S.f32(cfg.CLASS_THRESH), S.ptr(cls_prob), S.ptr(cls_pred),
+                                              S.ptr(det), S.stream()), "detect_decode")
+            self._rec_end(tok)
+            out.update(cls_score=cls_score, bbox_pred=bbox_pred, cls_prob=cls_prob, cls_pred=cls_pred, det=det)
+        return out
+
+    def _graph_state(self, key, dims, n_views, feat_c, dev):
+        """Static input buffers + captured graph of `_static_stage` for one input shape."""
+        st = self._graphs.get(key)
+        if st is not None:
+            return st
+        w, h = int(cfg.DEPTH_SHAPE[0]), int(cfg.DEPTH_SHAPE[1])
+        st = dict(scene=torch.zeros(1, 2, *dims, dtype=torch.float32, device=dev))
+        if cfg.USE_IMAGES:
+            st.update(feats=torch.zeros(n_views, feat_c, h, w, dtype=torch.float32, device=dev),
+                      depths=torch.zeros(n_views, h, w, dtype=torch.float32, device=dev),
+                      vp=torch.zeros(n_views, 40, dtype=torch.float32, device=dev))
+        st["graph"] = None
+        self._graphs[key] = st
+        return st
+
     def forward(self, blobs, mode="TEST", killing_inds=None):
         if mode != "TEST":
             raise NotImplementedError("only the inference (TEST) forward is implemented on the B200 path")
+        if not (cfg.USE_BACKBONE and cfg.USE_RPN):
+            raise NotImplementedError("USE_BACKBONE/USE_RPN=False (ground-truth RoIs) are training/ablation modes")
         self._ensure_packed()
         dev = next(self.parameters()).device
         data = blobs["data"]
@@ -421,38 +517,58 @@ class Network(nn.Module):
         dims = tuple(int(v) for v in data.shape[2:])
         P = self._predictions
         with torch.no_grad():
-            scene_t = data.to(dev, torch.float32, non_blocking=True).contiguous()
+            lists = cfg.USE_IMAGES and "proj_ind_3d" in blobs
+            use_graph = self._use_graph and not (self._keep_debug or self._prof is not None or lists)
+            if cfg.USE_IMAGES and not cfg.USE_IMAGES_GT:
+                use_graph = False
+            fused = None
+            if cfg.USE_IMAGES and not lists:
+                imgs = blobs["nearest_images"]
+                w, h = int(cfg.DEPTH_SHAPE[0]), int(cfg.DEPTH_SHAPE[1])
+                vp = proj.view_params(cfg.INTRINSIC, (w, h), cfg.PROJ_DEPTH_MIN, cfg.PROJ_DEPTH_MAX, dims, None,
+                                      imgs["poses"][0], imgs["world2grid"][0])
+                fused = dict(vp=vp, feats=imgs["images"][0], depths=torch.as_tensor(imgs["depths"][0]))
+            if use_graph:
+                nv = fused["feats"].shape[0] if fused else 0
+                fc = fused["feats"].shape[1] if fused else 0
+                st = self._graph_state((dims, nv, fc, self._math), dims, nv, fc, dev)
+                st["scene"].copy_(data, non_blocking=True)
+                if fused:
+                    st["feats"].copy_(fused["feats"], non_blocking=True)
+                    st["depths"].copy_(fused["depths"], non_blocking=True)
+                    st["vp"].copy_(fused["vp"], non_blocking=True)
+                    fdev = dict(vp=st["vp"], feats=st["feats"], depths=st["depths"])
+                else:
+                    fdev = None
+                if st["graph"] is None:
+                    # eager warm-up (fills the region/constant caches, sets kernel attributes), then capture
+                    self._static_stage(st["scene"], dims, blobs, None, fdev)
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        st["outs"] = self._static_stage(st["scene"], dims, blobs, None, fdev)
+                    st["graph"] = g
+                st["graph"].replay()
+                outs = {k: v.clone() for k, v in st["outs"].items()}  # results must not alias the replay buffers
+                scene_t = st["scene"]
+            else:
+                scene_t = data.to(dev, torch.float32, non_blocking=True).contiguous()
+                if fused:
+                    fused = dict(vp=fused["vp"].to(dev, non_blocking=True),
+                                 feats=fused["feats"].to(dev, torch.float32, non_blocking=True),
+                                 depths=fused["depths"].to(dev, torch.float32, non_blocking=True).contiguous())
+                outs = self._static_stage(scene_t, dims, blobs, killing_inds, fused)
             self._scene = scene_t
-            scene = Act(scene_t, dims, 2, layout="ncdhw")
-            imageft = None
-            if cfg.USE_IMAGES:
-                imageft = self._backproject(blobs, killing_inds, dims, dev)
-                self._imageft_vc = imageft.t if self._keep_debug else None
-            level1, level2 = self._backbone(scene, imageft) if cfg.USE_BACKBONE else (None, None)
-            if self._keep_debug:
-                P["level1_vc"], P["level2_vc"] = level1.t, level2.t
-            if not cfg.USE_RPN:
-                raise NotImplementedError("USE_RPN=False (ground-truth boxes as RoIs) is a training/ablation mode")
-            rois, scores, level_ids, num = self._region_proposal((level1, level2, None), dims)
-            det = None
-            if cfg.USE_CLASS:
-                cls_score, bbox_pred = self._classify((level1, level2, None), rois, level_ids)
-                R, nc = rois.shape[0], int(cfg.NUM_CLASSES)
-                cls_prob = torch.empty(R, nc, dtype=torch.float32, device=dev)
-                cls_pred = torch.empty(R, dtype=torch.int64, device=dev)
-                det = torch.empty(R, 16, dtype=torch.float32, device=dev)
-                S.check(S.lib.sis3d_detect_decode(S.ptr(rois), S.ptr(num), R, S.ptr(cls_score), S.ptr(bbox_pred), nc,
-                                                  *dims, S.f32(cfg.CLASS_THRESH), S.ptr(cls_prob), S.ptr(cls_pred),
-                                                  S.ptr(det), S.stream()), "detect_decode")
             # the one host round trip of the forward: RoI count + decoded detections (<= 13 KB)
-            n = int(num.item())
-            P["rois"], P["roi_scores"], P["level_inds"] = [rois[:n]], [scores[:n].view(-1, 1)], [level_ids[:n].float()]
+            n = int(outs["num"].item())
+            P["rois"], P["roi_scores"] = [outs["rois"][:n]], [outs["scores"][:n].view(-1, 1)]
+            P["level_inds"] = [outs["level_ids"][:n].float()]
             if cfg.USE_CLASS:
-                P["cls_score"], P["cls_pred"], P["cls_prob"] = cls_score[:n], cls_pred[:n], cls_prob[:n]
-                P["bbox_pred"] = bbox_pred[:n]
-                P["detections"] = det[:n]
+                P["cls_score"], P["cls_pred"], P["cls_prob"] = outs["cls_score"][:n], outs["cls_pred"][:n], outs["cls_prob"][:n]
+                P["bbox_pred"] = outs["bbox_pred"][:n]
+                P["detections"] = outs["det"][:n]
                 if cfg.USE_MASK:
-                    det_host = det[:n].cpu().numpy() if n else np.zeros((0, 16), np.float32)
+                    det_host = outs["det"][:n].cpu().numpy() if n else np.zeros((0, 16), np.float32)
                     P["mask_pred"] = [self._mask_branch(scene_t, det_host, n)]
                     P["detections_host"] = det_host
         return P

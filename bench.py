@@ -264,6 +264,13 @@ def main():
     e2e_v = world * args.steps / (ms_e2e / 1e3)
     conv_ms = sum(v[0] for k, v in prof.items() if k.startswith("conv"))
     top = sorted(prof.items(), key=lambda kv: -kv[1][0])[:6]
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"kernel_times_{math}.json"), "w") as f:
+            json.dump({k: {"ms_per_step": v[0], "launch_groups_per_step": v[1]} for k, v in
+                       sorted(prof.items(), key=lambda kv: -kv[1][0])}, f, indent=1)
+    except Exception:
+        pass
     alg = ALG_BYTES + MASK_BYTES_PER_VOXEL * vox
     kernel_ms = sum(v[0] for v in prof.values())
     out = {

@@ -110,6 +110,7 @@ typedef struct sis3d_region {
     int32_t in_dim[3];     /* input extent (x,y,z): taps outside read as zero */
     int32_t out_dim[3];    /* output extent */
     int64_t in_stride[3];  /* input voxel strides in elements (x,y,z) */
+    int64_t out_stride[3]; /* output voxel strides in elements; all zero = dense rows (m * out_ld) */
     int32_t tile_begin;    /* first M-tile of this region (exclusive prefix sum of tile counts) */
     int32_t pad_;
 } sis3d_region;
@@ -120,6 +121,13 @@ int sis3d_conv3d(const float *in, int64_t in_chan_stride, const float *w_packed,
                  const float *residual, int res_ld, int res_coff, float *out, int out_ld, int out_coff,
                  const sis3d_region *regions, int n_regions, int n_tiles, int cin, int cout, int ks,
                  int stride, int pad, int act, void *stream);
+/* Fully connected layer y[M][N] = act(x[M][K] . W + b) for the RoI classifier MLP (lib/nets/backbones.py:
+ * 92-96,225-231): split-K over `splits` CTAs-per-tile with a deterministic second-pass reduction.
+ * w_packed from sis3d_pack_conv_weight(ks=1).  workspace >= sis3d_linear_workspace_bytes(M,N,K). */
+size_t sis3d_linear_workspace_bytes(int M, int N, int K);
+int sis3d_linear(const float *x, const float *w_packed, const float *bias, float *y, int M, int K, int N,
+                 int act, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Tensor-core path for the 3x3x3 / stride 1 / pad 1 layers (same call sites as sis3d_conv3d):
  * tcgen05.mma kind::tf32 with fp32 accumulation in TMEM, operands staged by 4-D/2-D TMA boxes

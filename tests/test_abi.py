@@ -19,7 +19,7 @@ def test_header_symbols_exported():
 
 def test_region_struct_layout():
     from lib import _sis3d as S
-    assert S.REGION_BYTES == 80  # 3*8 + 3*4 + 3*4 + 3*8 + 4 + 4
+    assert S.REGION_BYTES == 104  # 3*8 + 3*4 + 3*4 + 3*8 + 3*8 + 4 + 4
 
 
 def test_no_cpu_fallback():

@@ -414,3 +414,26 @@ def test_conv3d_tc_tile_list(S):
     for (x0, c), s in zip(crops, sizes):
         mask[x0:x0 + s[0], :s[1], :s[2]] = False
     assert not out.cpu()[mask].any()
+
+
+@pytest.mark.parametrize("M,K,N,act", [(200, 8192, 256, 1), (200, 256, 128, 1), (200, 128, 19, 0), (200, 128, 114, 0), (7, 64, 5, 0)])
+def test_linear_split_k(S, M, K, N, act):
+    rng = np.random.default_rng(M + K + N)
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    w = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    ref = torch.from_numpy(x) @ torch.from_numpy(w).T + torch.from_numpy(b)
+    if act:
+        ref = F.relu(ref)
+    ldw = (N + 3) // 4 * 4
+    packed = torch.empty(K, ldw, device=DEV)
+    S.check(S.lib.sis3d_pack_conv_weight(S.ptr(torch.from_numpy(w).to(DEV).reshape(N, K, 1, 1, 1).contiguous()), N, K, 1,
+                                         S.ptr(packed), S.stream()))
+    y = torch.empty(M, N, device=DEV)
+    nbytes = int(S.lib.sis3d_linear_workspace_bytes(M, N, K))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    for _ in range(2):  # twice: deterministic reduction order
+        S.check(S.lib.sis3d_linear(S.ptr(torch.from_numpy(x).to(DEV)), S.ptr(packed), S.ptr(torch.from_numpy(b).to(DEV)), S.ptr(y),
+                                   M, K, N, act, S.ptr(ws), C.c_size_t(nbytes), S.stream()))
+        torch.cuda.synchronize()
+        torch.testing.assert_close(y.cpu(), ref, atol=3e-5, rtol=1e-4)
