@@ -83,6 +83,27 @@ def f32(x):
     return C.c_float(float(x))
 
 
+import numpy as _np
+
+REGION_DTYPE = _np.dtype({"names": ["in_off", "out_off", "res_off", "in_dim", "out_dim", "in_stride", "out_stride", "tile_begin", "pad_"],
+                          "formats": ["<i8", "<i8", "<i8", ("<i4", 3), ("<i4", 3), ("<i8", 3), ("<i8", 3), "<i4", "<i4"],
+                          "offsets": [0, 8, 16, 24, 36, 48, 72, 96, 100], "itemsize": 104})
+
+
+def regions_array(in_off, out_off, in_dim, out_dim, in_stride, out_stride=None):
+    """Vectorised builder of a sis3d_region table (numpy structured array matching the C struct) + tile count."""
+    n = len(in_off)
+    a = _np.zeros(n, dtype=REGION_DTYPE)
+    a["in_off"], a["out_off"] = in_off, out_off
+    a["in_dim"], a["out_dim"], a["in_stride"] = in_dim, out_dim, in_stride
+    if out_stride is not None:
+        a["out_stride"] = out_stride
+    m = _np.prod(_np.asarray(out_dim, dtype=_np.int64).reshape(n, 3), axis=1)
+    t = (m + TILE_M - 1) // TILE_M
+    a["tile_begin"] = _np.concatenate([[0], _np.cumsum(t)[:-1]])
+    return a, int(t.sum())
+
+
 def make_regions(entries, device):
     """entries: list of dict(in_off,out_off,res_off,in_dim,out_dim,in_stride) -> (device uint8 tensor, n_tiles)."""
     arr = (Region * len(entries))()

@@ -69,6 +69,8 @@ class Network(nn.Module):
         # conv math for the 3x3x3 layers: 'tf32' = tcgen05 tensor cores (default), 'fp32' = CUDA-core exact path
         self._math = os.environ.get("SIS3D_CONV_MATH", str(cfg.get("CONV_MATH", "tf32"))).lower()
         self._graphs = {}
+        self._pack_dirty = True
+        self._arena = {}  # grow-only device/pinned workspaces for the ragged (per-scene sized) stage
         self._use_graph = os.environ.get("SIS3D_CUDA_GRAPH", "1") != "0"
         self._prof = None  # name -> [(start_event, end_event)] when per-kernel timing is on (bench.py)
 
@@ -120,6 +122,23 @@ class Network(nn.Module):
             self.image_enet_fixed = self.image_enet_trainable = None
 
     # ------------------------------------------------------------------ packed weights
+    def load_state_dict(self, *a, **k):
+        self._pack_dirty = True
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):  # .cuda() / .to() / .float() move parameters -> repack
+        self._pack_dirty = True
+        return super()._apply(fn, *a, **k)
+
+    def _ws(self, name, numel, dtype, dev, pinned=False):
+        """Grow-only workspace: steady-state forwards never hit cudaMalloc for per-scene sized buffers."""
+        t = self._arena.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            cap = int(numel * 1.5) + 1024
+            t = torch.empty(cap, dtype=dtype, pin_memory=True) if pinned else torch.empty(cap, dtype=dtype, device=dev)
+            self._arena[name] = t
+        return t[:numel]
+
     def _version(self):
         return tuple((n, p._version, p.data_ptr()) for n, p in self.named_parameters())
 
@@ -128,7 +147,10 @@ class Network(nn.Module):
             raise S.Sis3dError("the sm_100a hot path needs a CUDA device (no CPU fallback)")
         if next(self.parameters()).device.type != "cuda":
             self.cuda()
+        if not self._pack_dirty and self._packed_version is not None:
+            return
         v = self._version()
+        self._pack_dirty = False
         if v == self._packed_version:
             return
         self._packed, self._packed_tc = {}, {}
@@ -385,72 +407,90 @@ class Network(nn.Module):
 
     def _mask_branch(self, scene_ncdhw, det_host, n):
         """Ragged per-RoI mask head (reference: network.py:283-317).  All kept crops are packed along x on
-        one zero-initialised canvas [sum(w_j + 1), max h, max l, 64] (one zero slab between crops = the
-        crop-border zero padding), so each of the six layers is ONE launch: layer 1 (C_in = 2, windowed
-        NCDHW scene) and the 1x1 head on the fp32 CUDA-core kernel, the four 64->64 3x3x3 layers on the
-        tcgen05 kernel driven by an explicit list of 8x4x4 bricks."""
-        keep = [i for i in range(n) if det_host[i, 8] > 0.5]
-        if not keep:
+        one zeroed canvas [sum(w_j + 1), max h, max l, 64] (one zero slab between crops = the crop-border
+        zero padding), so each of the six layers is ONE launch: layer 1 (C_in = 2, windowed NCDHW scene) and
+        the 1x1 head on the fp32 CUDA-core kernel, the four 64->64 3x3x3 layers on the tcgen05 kernel driven
+        by an explicit list of 8x4x4 bricks.  Tables are built vectorised on the host and shipped in ONE
+        pinned H2D copy; all buffers come from a grow-only arena."""
+        keep = np.nonzero(det_host[:n, 8] > 0.5)[0]
+        if keep.size == 0:
             return []
         dev = scene_ncdhw.device
-        X, Y, Z = scene_ncdhw.shape[2:]
-        crops = [[int(v) for v in det_host[i, 9:15]] for i in keep]
-        sizes = [(c[3] - c[0], c[4] - c[1], c[5] - c[2]) for c in crops]
-        vox = [s[0] * s[1] * s[2] for s in sizes]
-        offs = np.concatenate([[0], np.cumsum(vox)]).astype(np.int64)
+        X, Y, Z = (int(v) for v in scene_ncdhw.shape[2:])
+        crops = det_host[keep, 9:15].astype(np.int64)
+        sizes = crops[:, 3:6] - crops[:, 0:3]
+        vox = sizes.prod(1)
+        offs = np.concatenate([[0], np.cumsum(vox)])
         total = int(offs[-1])
+        nk = len(keep)
         ncls = self._packed["mask_backbone.geometry.10"][2]
-        outb = torch.empty(total * ncls, dtype=torch.float32, device=dev)
+        outb = torch.empty(total * ncls, dtype=torch.float32, device=dev)  # handed to the caller (mask_pred views)
         scene = Act(scene_ncdhw, (X, Y, Z), 2, layout="ncdhw")
+        scene_off = (crops[:, 0] * Y + crops[:, 1]) * Z + crops[:, 2]
+        scene_str = np.tile(np.array([Y * Z, Z, 1], dtype=np.int64), (nk, 1))
         use_tc = self._math == "tf32" and "mask_backbone.geometry.2" in self._packed_tc
         if use_tc:
-            Yc, Zc = max(s[1] for s in sizes), max(s[2] for s in sizes)
-            xoff = np.concatenate([[0], np.cumsum([s[0] + 1 for s in sizes])]).astype(np.int64)
+            Yc, Zc = int(sizes[:, 1].max()), int(sizes[:, 2].max())
+            xoff = np.concatenate([[0], np.cumsum(sizes[:, 0] + 1)])
             Xc = int(xoff[-1])
-            cs = (Yc * Zc * 64, Zc * 64, 64)  # canvas voxel strides
-            bufs = [torch.zeros(Xc, Yc, Zc, 64, dtype=torch.float32, device=dev) for _ in range(2)]
-            first = S.make_regions([dict(in_off=(c[0] * Y + c[1]) * Z + c[2], out_off=int(xoff[j]) * cs[0], in_dim=s,
-                                         out_dim=s, in_stride=(Y * Z, Z, 1), out_stride=cs)
-                                    for j, (c, s) in enumerate(zip(crops, sizes))], dev)
-            last = S.make_regions([dict(in_off=int(xoff[j]) * cs[0], out_off=int(offs[j]) * ncls, in_dim=s, out_dim=s,
-                                        in_stride=cs) for j, s in enumerate(sizes)], dev)
-            tiles = []
-            for j, s in enumerate(sizes):
-                x0 = int(xoff[j])
-                for bx in range(0, s[0], 8):
-                    for by in range(0, s[1], 4):
-                        for bz in range(0, s[2], 4):
-                            tiles.append((x0 + bx, by, bz, x0 + s[0], s[1], s[2], 0, 0))
-            tiles_t = torch.tensor(tiles, dtype=torch.int32).to(dev, non_blocking=True)
-            x = self._conv(scene, "mask_backbone.geometry.0", act=1, regions=first, out_dims=(Xc, Yc, Zc),
+            cs = np.array([Yc * Zc * 64, Zc * 64, 64], dtype=np.int64)
+            cstr = np.tile(cs, (nk, 1))
+            first, t_first = S.regions_array(scene_off, xoff[:-1] * cs[0], sizes, sizes, scene_str, cstr)
+            last, t_last = S.regions_array(xoff[:-1] * cs[0], offs[:-1] * ncls, sizes, sizes, cstr)
+            # brick list: every 8x4x4 brick of every crop
+            nb = (sizes + np.array([7, 3, 3])) // np.array([8, 4, 4])
+            cnt = nb.prod(1)
+            owner = np.repeat(np.arange(nk), cnt)
+            local = np.arange(int(cnt.sum())) - np.repeat(np.concatenate([[0], np.cumsum(cnt)[:-1]]), cnt)
+            bz = local % nb[owner, 2]
+            by = (local // nb[owner, 2]) % nb[owner, 1]
+            bx = local // (nb[owner, 2] * nb[owner, 1])
+            tiles = np.zeros((len(owner), 8), dtype=np.int32)
+            tiles[:, 0], tiles[:, 1], tiles[:, 2] = xoff[owner] + bx * 8, by * 4, bz * 4
+            tiles[:, 3], tiles[:, 4], tiles[:, 5] = xoff[owner] + sizes[owner, 0], sizes[owner, 1], sizes[owner, 2]
+            blob = np.concatenate([first.view(np.uint8), last.view(np.uint8), tiles.view(np.uint8).reshape(-1)])
+        else:
+            dstr = np.stack([sizes[:, 1] * sizes[:, 2] * 64, sizes[:, 2] * 64, np.full(nk, 64)], 1)
+            first, t_first = S.regions_array(scene_off, offs[:-1] * 64, sizes, sizes, scene_str)
+            mid, t_mid = S.regions_array(offs[:-1] * 64, offs[:-1] * 64, sizes, sizes, dstr)
+            last, t_last = S.regions_array(offs[:-1] * 64, offs[:-1] * ncls, sizes, sizes, dstr)
+            blob = np.concatenate([first.view(np.uint8), last.view(np.uint8), mid.view(np.uint8)])
+        stage = self._ws("mask_tables_host", blob.size, torch.uint8, dev, pinned=True)
+        stage.numpy()[:] = blob
+        tables = self._ws("mask_tables", blob.size, torch.uint8, dev)
+        tables.copy_(stage, non_blocking=True)
+        rb = nk * S.REGION_BYTES
+        r_first, r_last, r_rest = tables[:rb], tables[rb:2 * rb], tables[2 * rb:]
+        if use_tc:
+            cvox = Xc * Yc * Zc
+            canv = self._ws("mask_canvas", 2 * cvox * 64, torch.float32, dev)
+            canv.zero_()
+            bufs = [canv[:cvox * 64], canv[cvox * 64:]]
+            x = self._conv(scene, "mask_backbone.geometry.0", act=1, regions=(r_first, t_first), out_dims=(Xc, Yc, Zc),
                            out=Act(bufs[0], (Xc, Yc, Zc), 64))
             for li, idx in enumerate((2, 4, 6, 8)):
                 name = f"mask_backbone.geometry.{idx}"
                 dst = Act(bufs[(li + 1) % 2], (Xc, Yc, Zc), 64)
                 tok = self._rec(f"conv_tc[{name}]")
                 S.check(S.lib.sis3d_conv3d_k3_tc(S.ptr(x.t), S.ptr(self._packed_tc[name]), None, None, 0, 0, S.ptr(dst.t), 64,
-                                                 0, Xc, Yc, Zc, 64, 64, S.ptr(tiles_t), len(tiles), 1, S.stream()),
+                                                 0, Xc, Yc, Zc, 64, 64, S.ptr(r_rest), tiles.shape[0], 1, S.stream()),
                         f"conv3d_k3_tc[{name}]")
                 self._rec_end(tok)
                 x = dst
         else:
-            bufs = [torch.empty(total * 64, dtype=torch.float32, device=dev) for _ in range(2)]
-            first = S.make_regions([dict(in_off=(c[0] * Y + c[1]) * Z + c[2], out_off=int(offs[j]) * 64, in_dim=s,
-                                         out_dim=s, in_stride=(Y * Z, Z, 1)) for j, (c, s) in enumerate(zip(crops, sizes))], dev)
-            mid = S.make_regions([dict(in_off=int(offs[j]) * 64, out_off=int(offs[j]) * 64, in_dim=s, out_dim=s,
-                                       in_stride=(s[1] * s[2] * 64, s[2] * 64, 64)) for j, s in enumerate(sizes)], dev)
-            last = S.make_regions([dict(in_off=int(offs[j]) * 64, out_off=int(offs[j]) * ncls, in_dim=s, out_dim=s,
-                                        in_stride=(s[1] * s[2] * 64, s[2] * 64, 64)) for j, s in enumerate(sizes)], dev)
-            x = self._conv(scene, "mask_backbone.geometry.0", act=1, regions=first, out_dims=(total, 1, 1),
+            act_buf = self._ws("mask_act", 2 * total * 64, torch.float32, dev)
+            bufs = [act_buf[:total * 64], act_buf[total * 64:]]
+            x = self._conv(scene, "mask_backbone.geometry.0", act=1, regions=(r_first, t_first), out_dims=(total, 1, 1),
                            out=Act(bufs[0], (total, 1, 1), 64))
             for li, idx in enumerate((2, 4, 6, 8)):
-                x = self._conv(x, f"mask_backbone.geometry.{idx}", act=1, regions=mid, out_dims=(total, 1, 1),
+                x = self._conv(x, f"mask_backbone.geometry.{idx}", act=1, regions=(r_rest, t_mid), out_dims=(total, 1, 1),
                                out=Act(bufs[(li + 1) % 2], (total, 1, 1), 64))
-        y = self._conv(x, "mask_backbone.geometry.10", pad=0, act=2, regions=last, out_dims=(total, 1, 1),
+        y = self._conv(x, "mask_backbone.geometry.10", pad=0, act=2, regions=(r_last, t_last), out_dims=(total, 1, 1),
                        out=Act(outb, (total, 1, 1), ncls))
         masks = []
-        for j, s in enumerate(sizes):
-            m = y.t[int(offs[j]) * ncls:int(offs[j + 1]) * ncls].view(s[0], s[1], s[2], ncls)
+        for j in range(nk):
+            w_, h_, l_ = (int(v) for v in sizes[j])
+            m = y.t[int(offs[j]) * ncls:int(offs[j + 1]) * ncls].view(w_, h_, l_, ncls)
             masks.append(m.permute(3, 0, 1, 2).unsqueeze(0))  # [1,ncls,w,h,l] view, reference layout
         return masks
 
@@ -536,7 +576,9 @@ class Network(nn.Module):
                 if fused:
                     st["feats"].copy_(fused["feats"], non_blocking=True)
                     st["depths"].copy_(fused["depths"], non_blocking=True)
-                    st["vp"].copy_(fused["vp"], non_blocking=True)
+                    vph = self._ws("vp_host", fused["vp"].numel(), torch.float32, dev, pinned=True)
+                    vph.copy_(fused["vp"].reshape(-1))
+                    st["vp"].copy_(vph.view_as(st["vp"]), non_blocking=True)
                     fdev = dict(vp=st["vp"], feats=st["feats"], depths=st["depths"])
                 else:
                     fdev = None

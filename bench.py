@@ -164,6 +164,7 @@ def main():
     ap.add_argument("--impl", default="sis3d")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-profile", type=int, default=0, help="cProfile N forwards -> gpurun_out/host_profile.txt")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -240,6 +241,23 @@ def main():
     for i in range(args.warmup):
         step(dev_in[i % n_in], False)
         step(host_in[i % n_in], True)
+    if args.host_profile and rank == 0:
+        import cProfile
+        import io
+        import pstats
+        pr = cProfile.Profile()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pr.enable()
+        for i in range(args.host_profile):
+            step(dev_in[i % n_in], False)
+        pr.disable()
+        wall = (time.perf_counter() - t0) / args.host_profile * 1e3
+        buf = io.StringIO()
+        pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(45)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "host_profile.txt"), "w") as f:
+            f.write(f"wall ms per forward (device-resident inputs): {wall:.3f}\n" + buf.getvalue())
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
