@@ -34,6 +34,20 @@ def view_params(intrinsic, image_dims, depth_min, depth_max, volume_dims, depths
 
     world_to_camera | grid_to_world | clamped frustum bounds (projection.py:56-60, 39-49), computed for
     all views in one batch of fp32 torch-CPU ops (bit-identical to the reference's per-view loop)."""
+    # These are a handful of 4x4 products: keep them on the calling thread.  Letting torch fan tiny ops out
+    # to its intra-op pool leaves dozens of spinning OpenMP workers behind, which on a CPU-quota'd
+    # container (cgroup cpu.max) gets the whole process throttled for ~80 ms at a time (measured).
+    nthreads = torch.get_num_threads()
+    if nthreads > 1:
+        torch.set_num_threads(1)
+    try:
+        return _view_params_impl(intrinsic, image_dims, depth_min, depth_max, volume_dims, poses, world2grid)
+    finally:
+        if nthreads > 1:
+            torch.set_num_threads(nthreads)
+
+
+def _view_params_impl(intrinsic, image_dims, depth_min, depth_max, volume_dims, poses, world2grid):
     poses = torch.as_tensor(poses, dtype=torch.float32).reshape(-1, 4, 4).cpu()
     n = poses.shape[0]
     w2g = torch.as_tensor(world2grid, dtype=torch.float32).cpu().reshape(-1, 4, 4)

@@ -69,6 +69,7 @@ class Network(nn.Module):
         # conv math for the 3x3x3 layers: 'tf32' = tcgen05 tensor cores (default), 'fp32' = CUDA-core exact path
         self._math = os.environ.get("SIS3D_CONV_MATH", str(cfg.get("CONV_MATH", "tf32"))).lower()
         self._graphs = {}
+        self._sparse_color = os.environ.get("SIS3D_SPARSE_COLOR", "1") != "0"
         self._pack_dirty = True
         self._arena = {}  # grow-only device/pinned workspaces for the ragged (per-scene sized) stage
         self._use_graph = os.environ.get("SIS3D_CUDA_GRAPH", "1") != "0"
@@ -334,6 +335,24 @@ class Network(nn.Module):
             n_pairs = torch.empty(1, dtype=torch.int32, device=dev)
             S.check(S.lib.sis3d_backproject_pairs(S.ptr(counts), n, S.ptr(pairs), S.ptr(n_pairs), S.stream()), "pairs")
             self._proj_counts = counts
+        first = self.SPEC["color"][0]
+        if (self._sparse_color and not self._keep_debug and first[0] == "k2s2" and feats.shape[1] % 16 == 0
+                and first[3] in (32, 64)):
+            # fused + sparse: never materialise the back-projected volume (csrc/sparse.cu)
+            packed, _, cout, cin, _ = self._packed[f"color.{first[1]}"]
+            od = tuple(d // 2 for d in dims)
+            out = Act(torch.empty(*od, cout, dtype=torch.float32, device=dev), od, cout)
+            feats = feats.contiguous()
+            feats_t = torch.empty(feats.shape[0], w * h, feats.shape[1], dtype=torch.float32, device=dev)
+            nbytes = int(S.lib.sis3d_backproject_conv_k2s2_workspace_bytes(*dims, cout))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            tok = self._rec("backproject_conv_k2s2")
+            S.check(S.lib.sis3d_backproject_conv_k2s2(S.ptr(feats), S.ptr(feats_t), S.ptr(pix), S.ptr(pairs), S.ptr(n_pairs),
+                                                      feats.shape[0], feats.shape[1], w, h, *dims, S.ptr(packed), cout,
+                                                      S.ptr(out.t), out.ld, 0, S.ptr(ws), C.c_size_t(nbytes), S.stream()),
+                    "backproject_conv_k2s2")
+            self._rec_end(tok)
+            return ("color0", out)
         tok = self._rec("backproject_max")
         vol = proj.backproject(feats, pix, pairs, n_pairs, dims, w, h)
         self._rec_end(tok)
@@ -347,8 +366,12 @@ class Network(nn.Module):
         if cfg.USE_IMAGES:
             d4 = tuple((d // 2) // 2 for d in scene.dims)
             level1 = Act(torch.empty(*d4, 128, dtype=torch.float32, device=dev), d4, 128)
-            self._run_stack(imageft, "color", spec["color"],
-                            final_out=lambda x, op: Act(level1.t, d4, 64, ld=128, coff=0))
+            if isinstance(imageft, tuple):  # ("color0", act): color.0 already produced by the fused sparse path
+                self._run_stack(imageft[1], "color", spec["color"][1:],
+                                final_out=lambda x, op: Act(level1.t, d4, 64, ld=128, coff=0))
+            else:
+                self._run_stack(imageft, "color", spec["color"],
+                                final_out=lambda x, op: Act(level1.t, d4, 64, ld=128, coff=0))
             self._run_stack(scene, "geometry1", spec["geometry1"],
                             final_out=lambda x, op: Act(level1.t, d4, 64, ld=128, coff=64))
         else:
@@ -505,7 +528,7 @@ class Network(nn.Module):
         imageft = None
         if cfg.USE_IMAGES:
             imageft = self._backproject(blobs, killing_inds, dims, dev, fused)
-            self._imageft_vc = imageft.t if self._keep_debug else None
+            self._imageft_vc = imageft.t if (self._keep_debug and not isinstance(imageft, tuple)) else None
         level1, level2 = self._backbone(scene, imageft)
         if self._keep_debug:
             P["level1_vc"], P["level2_vc"] = level1.t, level2.t

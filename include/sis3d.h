@@ -93,6 +93,18 @@ int sis3d_backproject_max(const float *feats, float *feats_t, const int16_t *pix
                           const int32_t *pairs, const int32_t *n_pairs, int n_views, int C,
                           int img_w, int img_h, int X, int Y, int Z, float *volume_vc, void *stream);
 
+/* Back-projection fused with the first colour convolution (2x2x2, stride 2, no bias, ReLU;
+ * lib/nets/backbones.py:203 / :137): out = relu(conv3d(max-over-views back-projection, W, stride 2))
+ * WITHOUT materialising the (>= 95 % zero) feature volume: covered voxels are listed per tap, multiplied by
+ * that tap's weight slice and combined per output voxel in tap order (csrc/sparse.cu).  Arguments as for
+ * sis3d_backproject_max; w_packed from sis3d_pack_conv_weight(ks=2) ([8*C][cout]); out is VC
+ * [X/2][Y/2][Z/2][cout] with row stride out_ld / channel offset out_coff.  C % 16 == 0, cout in {32,64}. */
+size_t sis3d_backproject_conv_k2s2_workspace_bytes(int X, int Y, int Z, int cout);
+int sis3d_backproject_conv_k2s2(const float *feats, float *feats_t, const int16_t *pix, const int32_t *pairs,
+                                const int32_t *n_pairs, int n_views, int C, int img_w, int img_h, int X,
+                                int Y, int Z, const float *w_packed, int cout, float *out, int out_ld,
+                                int out_coff, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * 3D convolution (implicit GEMM) over a table of regions.  Replaces the nn.Conv3d call sites of
  * lib/nets/backbones.py:20-22,126-169,188-231,241-272 and lib/nets/network.py:40-52 (cuDNN in the

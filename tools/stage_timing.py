@@ -4,6 +4,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (os.path.join(ROOT, "3d-sis_b200"), ROOT, os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import numpy as np, torch
+if os.environ.get("SIS3D_HOST_THREADS"):
+    torch.set_num_threads(int(os.environ["SIS3D_HOST_THREADS"]))
+print("torch threads", torch.get_num_threads(), "cpu_count", os.cpu_count(), "affinity", len(os.sched_getaffinity(0)))
 import bench
 from test_gpu_forward import make_net
 from test_oracle_golden import CASES
@@ -77,3 +80,10 @@ def seq():
     return net._mask_branch(st["scene"], dh, nn)
 T("all of the above, one sync", seq)
 T("net.forward", lambda: net.forward(blobs, "TEST", None))
+
+ts = []
+for _ in range(60):
+    torch.cuda.synchronize(); t0 = time.perf_counter(); net.forward(blobs, "TEST", None); torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) * 1e3)
+ts = np.array(ts)
+print("net.forward x60: mean %.3f median %.3f min %.3f max %.3f  | >4ms: %d" % (ts.mean(), np.median(ts), ts.min(), ts.max(), (ts > 4).sum()))
+print("   trace:", " ".join("%.1f" % t for t in ts[:30]))
