@@ -1,4 +1,4 @@
-// conv_tc.cu -- 3x3x3 / stride-1 / pad-1 convolution as an implicit GEMM on the 5th-gen tensor cores.
+// conv_tc.cu -- 3x3x3 (pad 1) and 1x1x1 stride-1 convolutions as an implicit GEMM on the 5th-gen tensor cores.
 //
 //   D[128 voxels x BN] (TMEM, fp32)  +=  A[128 x 32] (smem, TF32)  x  B[BN x 32]^T (smem, TF32)
 //
@@ -102,7 +102,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-template <int BN>
+template <int BN, int KS>
 __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
     constexpr int B_BYTES = BN * 128;
@@ -142,7 +142,9 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
     }
     const int n0 = blockIdx.y * BN;
     const int kchunks = a.cin / TC_KC;
-    const int total = 27 * kchunks;
+    constexpr int TAPS = KS * KS * KS;  // 27 (3x3x3, pad 1) or 1 (1x1x1)
+    constexpr int SHIFT = KS == 3 ? 1 : 0;
+    const int total = TAPS * kchunks;
 
     if (threadIdx.x == 0) {
         // ===== TMA producer =====
@@ -152,9 +154,9 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
             mbar_wait(empty + s, ph ^ 1);
             mbar_expect_tx(full + s, STAGE_BYTES);
             const int tap = it / kchunks, kc = it - tap * kchunks;
-            const int dx = tap / 9, dy = (tap / 3) % 3, dz = tap % 3;
+            const int dx = tap / (KS * KS), dy = (tap / KS) % KS, dz = tap % KS;
             uint8_t *sa = smem + s * STAGE_BYTES;
-            tma_load_4d(sa, &tmA, full + s, kc * TC_KC, z0 + dz - 1, y0 + dy - 1, x0 + dx - 1);
+            tma_load_4d(sa, &tmA, full + s, kc * TC_KC, z0 + dz - SHIFT, y0 + dy - SHIFT, x0 + dx - SHIFT);
             tma_load_2d(sa + TC_A_BYTES, &tmB, full + s, tap * a.cin + kc * TC_KC, n0);
         }
     } else if (threadIdx.x == 32) {
@@ -213,13 +215,13 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
 }
 
 // weights [cout][cin][3][3][3] -> [cout][27*cin] with k = tap*cin + c
-__global__ void pack_conv_weight_tc_kernel(const float *w, int cout, int cin, float *out) {
-    const int64_t total = (int64_t)cout * 27 * cin;
+__global__ void pack_conv_weight_tc_kernel(const float *w, int cout, int cin, int taps, float *out) {
+    const int64_t total = (int64_t)cout * taps * cin;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % cin);
-        const int tap = (int)((i / cin) % 27);
-        const int n = (int)(i / ((int64_t)cin * 27));
-        out[i] = w[((int64_t)n * cin + c) * 27 + tap];
+        const int tap = (int)((i / cin) % taps);
+        const int n = (int)(i / ((int64_t)cin * taps));
+        out[i] = w[((int64_t)n * cin + c) * taps + tap];
     }
 }
 
@@ -237,27 +239,28 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-template <int BN>
+template <int BN, int KS>
 static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcArgs &a, int n_tiles, cudaStream_t s) {
     const size_t smem = (size_t)TC_STAGES * (TC_A_BYTES + BN * 128) + 1024 + 256;
     static bool attr_done = false;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(conv3d_k3_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(conv3d_k3_tc_kernel<BN, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return SIS3D_ELAUNCH;
         attr_done = true;
     }
     dim3 grid(n_tiles, a.cout / BN);
-    conv3d_k3_tc_kernel<BN><<<grid, 128, smem, s>>>(tmA, tmB, a);
+    conv3d_k3_tc_kernel<BN, KS><<<grid, 128, smem, s>>>(tmA, tmB, a);
     return finish_launch();
 }
 
 }  // namespace sis3d
 using namespace sis3d;
 
-extern "C" int sis3d_pack_conv_weight_tc(const float *w, int cout, int cin, float *w_tc, void *stream) {
-    if (!w || !w_tc || cout <= 0 || cin <= 0) return SIS3D_EINVAL;
-    const int64_t total = (int64_t)cout * 27 * cin;
-    pack_conv_weight_tc_kernel<<<(int)imin64(cdiv64(total, 256), 148 * 8), 256, 0, (cudaStream_t)stream>>>(w, cout, cin, w_tc);
+extern "C" int sis3d_pack_conv_weight_tc(const float *w, int cout, int cin, int ks, float *w_tc, void *stream) {
+    if (!w || !w_tc || cout <= 0 || cin <= 0 || (ks != 1 && ks != 3)) return SIS3D_EINVAL;
+    const int taps = ks * ks * ks;
+    const int64_t total = (int64_t)cout * taps * cin;
+    pack_conv_weight_tc_kernel<<<(int)imin64(cdiv64(total, 256), 148 * 8), 256, 0, (cudaStream_t)stream>>>(w, cout, cin, taps, w_tc);
     return finish_launch();
 }
 
@@ -267,8 +270,9 @@ extern "C" int sis3d_conv3d_k3_tc_supported(int cin, int cout) {
 
 extern "C" int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const float *bias, const float *residual, int res_ld,
                                   int res_coff, float *out, int out_ld, int out_coff, int X, int Y, int Z, int cin, int cout,
-                                  const int32_t *tiles, int n_tiles, int act, void *stream) {
-    if (!in || !w_tc || !out || X <= 0 || Y <= 0 || Z <= 0) return SIS3D_EINVAL;
+                                  int ks, const int32_t *tiles, int n_tiles, int act, void *stream) {
+    if (!in || !w_tc || !out || X <= 0 || Y <= 0 || Z <= 0 || (ks != 1 && ks != 3)) return SIS3D_EINVAL;
+    const int taps = ks * ks * ks;
     if (!sis3d_conv3d_k3_tc_supported(cin, cout)) return SIS3D_EUNSUPPORTED;
     if (((uintptr_t)in | (uintptr_t)w_tc | (uintptr_t)out) & 15) return SIS3D_EINVAL;
     if ((out_ld | out_coff | res_ld | res_coff) & 3) return SIS3D_EINVAL;
@@ -286,8 +290,8 @@ extern "C" int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const floa
             return SIS3D_EINVAL;
     }
     {
-        cuuint64_t dims[2] = {(cuuint64_t)27 * cin, (cuuint64_t)cout};
-        cuuint64_t strides[1] = {(cuuint64_t)27 * cin * 4};
+        cuuint64_t dims[2] = {(cuuint64_t)taps * cin, (cuuint64_t)cout};
+        cuuint64_t strides[1] = {(cuuint64_t)taps * cin * 4};
         cuuint32_t box[2] = {TC_KC, (cuuint32_t)BN};
         cuuint32_t estr[2] = {1, 1};
         if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)w_tc, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -302,9 +306,16 @@ extern "C" int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const floa
     if (!tiles) n_tiles = cdiv(X, TC_BX) * a.tiles_y * a.tiles_z;
     if (n_tiles <= 0) return SIS3D_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    if (ks == 3) {
+        switch (BN) {
+            case 32: return launch_tc<32, 3>(tmA, tmB, a, n_tiles, s);
+            case 64: return launch_tc<64, 3>(tmA, tmB, a, n_tiles, s);
+            default: return launch_tc<128, 3>(tmA, tmB, a, n_tiles, s);
+        }
+    }
     switch (BN) {
-        case 32: return launch_tc<32>(tmA, tmB, a, n_tiles, s);
-        case 64: return launch_tc<64>(tmA, tmB, a, n_tiles, s);
-        default: return launch_tc<128>(tmA, tmB, a, n_tiles, s);
+        case 32: return launch_tc<32, 1>(tmA, tmB, a, n_tiles, s);
+        case 64: return launch_tc<64, 1>(tmA, tmB, a, n_tiles, s);
+        default: return launch_tc<128, 1>(tmA, tmB, a, n_tiles, s);
     }
 }

@@ -118,6 +118,67 @@ __global__ void __launch_bounds__(128) roi_pool_vc_kernel(const float *feat1, co
     }
 }
 
+// Tail of the RoI classifier (lib/nets/backbones.py:225-231 layers 2,4 + lib/nets/network.py:55-57 heads) in one
+// launch: 8 RoI rows per CTA, activations stay in shared memory, weights ([K][ldw] packed) stream from L2.
+constexpr int kMlpRows = 8;
+__global__ void __launch_bounds__(256) mlp_tail_kernel(const float *x1, int R, int d1, const float *w2, const float *b2, int d2,
+                                                       const float *w3, const float *b3, int d3, const float *wc,
+                                                       const float *bc, int nc, const float *wb, const float *bb, int nb,
+                                                       float *cls_score, float *bbox_pred) {
+    __shared__ float sa[kMlpRows][256];
+    __shared__ float sb[kMlpRows][256];
+    const int r0 = blockIdx.x * kMlpRows, t = threadIdx.x;
+    for (int i = t; i < kMlpRows * d1; i += 256) {
+        const int r = i / d1, k = i - r * d1;
+        sa[r][k] = (r0 + r < R) ? x1[(int64_t)(r0 + r) * d1 + k] : 0.f;
+    }
+    __syncthreads();
+    float acc[kMlpRows];
+    if (t < d2) {  // layer 2: d1 -> d2, ReLU
+#pragma unroll
+        for (int r = 0; r < kMlpRows; ++r) acc[r] = 0.f;
+        const int ld = (d2 + 3) & ~3;
+        for (int k = 0; k < d1; ++k) {
+            const float w = __ldg(w2 + (int64_t)k * ld + t);
+#pragma unroll
+            for (int r = 0; r < kMlpRows; ++r) acc[r] = fmaf(sa[r][k], w, acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < kMlpRows; ++r) sb[r][t] = fmaxf(acc[r] + b2[t], 0.f);
+    }
+    __syncthreads();
+    if (t < d3) {  // layer 3: d2 -> d3, ReLU
+#pragma unroll
+        for (int r = 0; r < kMlpRows; ++r) acc[r] = 0.f;
+        const int ld = (d3 + 3) & ~3;
+        for (int k = 0; k < d2; ++k) {
+            const float w = __ldg(w3 + (int64_t)k * ld + t);
+#pragma unroll
+            for (int r = 0; r < kMlpRows; ++r) acc[r] = fmaf(sb[r][k], w, acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < kMlpRows; ++r) sa[r][t] = fmaxf(acc[r] + b3[t], 0.f);
+    }
+    __syncthreads();
+    for (int o = t; o < nc + nb; o += 256) {  // heads: d3 -> nc (class scores) | nb (box deltas)
+        const bool is_cls = o < nc;
+        const int n = is_cls ? o : o - nc;
+        const float *w = is_cls ? wc : wb;
+        const int ld = ((is_cls ? nc : nb) + 3) & ~3;
+#pragma unroll
+        for (int r = 0; r < kMlpRows; ++r) acc[r] = 0.f;
+        for (int k = 0; k < d3; ++k) {
+            const float wv = __ldg(w + (int64_t)k * ld + n);
+#pragma unroll
+            for (int r = 0; r < kMlpRows; ++r) acc[r] = fmaf(sa[r][k], wv, acc[r]);
+        }
+        const float bias = is_cls ? bc[n] : bb[n];
+#pragma unroll
+        for (int r = 0; r < kMlpRows; ++r)
+            if (r0 + r < R) (is_cls ? cls_score : bbox_pred)[(int64_t)(r0 + r) * (is_cls ? nc : nb) + n] = acc[r] + bias;
+    }
+}
+
 // one thread per RoI row
 __global__ void detect_decode_kernel(const float *rois, const int32_t *num_rois, int max_rois, const float *cls_score,
                                      const float *bbox_pred, int nc, int sx, int sy, int sz, float thresh, float *cls_prob,
@@ -212,5 +273,15 @@ extern "C" int sis3d_detect_decode(const float *rois, const int32_t *num_rois, i
     detect_decode_kernel<<<cdiv(max_rois, 128), 128, 0, (cudaStream_t)stream>>>(rois, num_rois, max_rois, cls_score, bbox_pred,
                                                                               num_classes, scene_x, scene_y, scene_z,
                                                                               class_thresh, cls_prob, cls_pred, det);
+    return finish_launch();
+}
+
+extern "C" int sis3d_mlp_tail(const float *x1, int R, int d1, const float *w2, const float *b2, int d2, const float *w3,
+                              const float *b3, int d3, const float *wc, const float *bc, int nc, const float *wb,
+                              const float *bb, int nb, float *cls_score, float *bbox_pred, void *stream) {
+    if (!x1 || !w2 || !b2 || !w3 || !b3 || !wc || !bc || !wb || !bb || !cls_score || !bbox_pred || R <= 0) return SIS3D_EINVAL;
+    if (d1 > 256 || d2 > 256 || d3 > 256 || d1 <= 0 || d2 <= 0 || d3 <= 0 || nc <= 0 || nb <= 0) return SIS3D_EUNSUPPORTED;
+    mlp_tail_kernel<<<cdiv(R, kMlpRows), 256, 0, (cudaStream_t)stream>>>(x1, R, d1, w2, b2, d2, w3, b3, d3, wc, bc, nc, wb, bb, nb,
+                                                                        cls_score, bbox_pred);
     return finish_launch();
 }

@@ -121,7 +121,7 @@ constexpr int kMaxLevels = 3;
 constexpr int kHistBins = 2048;
 struct RpnLevels {
     const float *cls[kMaxLevels], *deltas[kMaxLevels], *sizes[kMaxLevels];
-    int grid[kMaxLevels][3], A[kMaxLevels], cls_mode[kMaxLevels];
+    int grid[kMaxLevels][3], A[kMaxLevels], cls_mode[kMaxLevels], cls_ld[kMaxLevels], deltas_ld[kMaxLevels];
     int offset[kMaxLevels + 1];  // flat anchor index offsets
     int n_levels, feat_stride, scene[3], border;
 };
@@ -160,9 +160,9 @@ __global__ void __launch_bounds__(256) rpn_score_kernel(const RpnLevels L, unsig
             const int A = L.A[lvl];
             float p;
             if (L.cls_mode[lvl] == 1) {  // caller already holds foreground probabilities [N][A]
-                p = __ldg(L.cls[lvl] + (int64_t)vox * A + a);
+                p = __ldg(L.cls[lvl] + (int64_t)vox * L.cls_ld[lvl] + a);
             } else {  // 2-way softmax over {bg, fg} logits (lib/nets/network.py:546)
-                const float s0 = __ldg(L.cls[lvl] + (int64_t)vox * 2 * A + a), s1 = __ldg(L.cls[lvl] + (int64_t)vox * 2 * A + A + a);
+                const float s0 = __ldg(L.cls[lvl] + (int64_t)vox * L.cls_ld[lvl] + a), s1 = __ldg(L.cls[lvl] + (int64_t)vox * L.cls_ld[lvl] + A + a);
                 const float m = fmaxf(s0, s1);
                 const float e0 = expf(s0 - m), e1 = expf(s1 - m);
                 p = __fdiv_rn(e1, __fadd_rn(e0, e1));
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(1024) rpn_topk_decode_kernel(const RpnLevels L
             decode_flat(L, f, lvl, vox, a, x, y, z);
             lvl_id = lvl + 1;
             const float *sz = L.sizes[lvl] + a * 3;
-            const float *d = L.deltas[lvl] + ((int64_t)vox * L.A[lvl] + a) * 6;
+            const float *d = L.deltas[lvl] + (int64_t)vox * L.deltas_ld[lvl] + a * 6;
             const float st = (float)L.feat_stride;
             const float pos[3] = {st * x, st * y, st * z};
 #pragma unroll
@@ -363,6 +363,8 @@ extern "C" int sis3d_rpn_proposals(const sis3d_rpn_level *lv, int n_levels, int 
     for (int i = 0; i < n_levels; ++i) {
         if (!lv[i].cls || !lv[i].deltas || !lv[i].anchor_sizes || lv[i].num_anchors <= 0) return SIS3D_EINVAL;
         L.cls[i] = lv[i].cls; L.deltas[i] = lv[i].deltas; L.sizes[i] = lv[i].anchor_sizes; L.A[i] = lv[i].num_anchors; L.cls_mode[i] = lv[i].cls_mode;
+        L.cls_ld[i] = lv[i].cls_ld ? lv[i].cls_ld : (lv[i].cls_mode == 1 ? lv[i].num_anchors : 2 * lv[i].num_anchors);
+        L.deltas_ld[i] = lv[i].deltas_ld ? lv[i].deltas_ld : 6 * lv[i].num_anchors;
         for (int k = 0; k < 3; ++k) L.grid[i][k] = lv[i].grid[k];
         L.offset[i] = total;
         total += lv[i].grid[0] * lv[i].grid[1] * lv[i].grid[2] * lv[i].num_anchors;

@@ -35,7 +35,8 @@ class Region(C.Structure):
 class RpnLevel(C.Structure):
     """struct sis3d_rpn_level (include/sis3d.h)."""
     _fields_ = [("cls", C.c_void_p), ("deltas", C.c_void_p), ("anchor_sizes", C.c_void_p),
-                ("grid", C.c_int32 * 3), ("num_anchors", C.c_int32), ("cls_mode", C.c_int32), ("pad_", C.c_int32)]
+                ("grid", C.c_int32 * 3), ("num_anchors", C.c_int32), ("cls_mode", C.c_int32), ("cls_ld", C.c_int32),
+                ("deltas_ld", C.c_int32), ("pad_", C.c_int32)]
 
 
 REGION_BYTES = C.sizeof(Region)
@@ -47,7 +48,7 @@ SYMBOLS = ["sis3d_strerror", "sis3d_version", "sis3d_launch_count", "sis3d_nms_w
            "sis3d_project_compact_workspace_bytes", "sis3d_backproject_pairs", "sis3d_project_scatter_lists",
            "sis3d_backproject_max", "sis3d_backproject_conv_k2s2_workspace_bytes", "sis3d_backproject_conv_k2s2",
            "sis3d_pack_conv_weight", "sis3d_conv3d", "sis3d_maxpool3",
-           "sis3d_vc_to_ncdhw", "sis3d_linear_workspace_bytes", "sis3d_linear", "sis3d_pack_conv_weight_tc", "sis3d_conv3d_k3_tc_supported", "sis3d_conv3d_k3_tc",
+           "sis3d_vc_to_ncdhw", "sis3d_linear_workspace_bytes", "sis3d_linear", "sis3d_mlp_tail", "sis3d_pack_conv_weight_tc", "sis3d_conv3d_k3_tc_supported", "sis3d_conv3d_k3_tc",
            "sis3d_rpn_workspace_bytes", "sis3d_rpn_proposals", "sis3d_detect_decode"]
 
 lib.sis3d_strerror.restype = C.c_char_p

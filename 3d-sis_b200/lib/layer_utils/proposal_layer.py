@@ -28,6 +28,7 @@ def rpn_proposals(levels, scene_dims, cfg_key="TEST", want_order=False):
         for k in range(3):
             arr[i].grid[k] = int(lv["grid"][k])
         arr[i].num_anchors, arr[i].cls_mode = int(lv["A"]), int(lv.get("cls_mode", 0))
+        arr[i].cls_ld, arr[i].deltas_ld = int(lv.get("cls_ld", 0)), int(lv.get("deltas_ld", 0))
     nbytes = int(S.lib.sis3d_rpn_workspace_bytes(arr, len(levels), pre))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     rois = torch.empty(post, 6, dtype=torch.float32, device=dev)

@@ -169,10 +169,19 @@ class Network(nn.Module):
             S.check(S.lib.sis3d_pack_conv_weight(S.ptr(w), cout, cin, ks, S.ptr(packed), S.stream()), "pack")
             b = params.get(base + ".bias")
             self._packed[base] = (packed, None if b is None else b.detach().float().contiguous(), cout, cin, ks)
-            if ks == 3 and S.lib.sis3d_conv3d_k3_tc_supported(cin, cout):
-                wtc = torch.empty(cout, 27 * cin, dtype=torch.float32, device=w.device)
-                S.check(S.lib.sis3d_pack_conv_weight_tc(S.ptr(w), cout, cin, S.ptr(wtc), S.stream()), "pack_tc")
+            if ks in (1, 3) and p.dim() == 5 and S.lib.sis3d_conv3d_k3_tc_supported(cin, cout):
+                wtc = torch.empty(cout, ks ** 3 * cin, dtype=torch.float32, device=w.device)
+                S.check(S.lib.sis3d_pack_conv_weight_tc(S.ptr(w), cout, cin, ks, S.ptr(wtc), S.stream()), "pack_tc")
                 self._packed_tc[base] = wtc
+        for lvl in (1, 2, 3):  # both RPN heads of a level as ONE 1x1 conv: [2A | 6A] output channels
+            c, b = f"rpn_cls_score_net_level{lvl}.0", f"rpn_bbox_pred_net_level{lvl}"
+            if c + ".weight" in params and b + ".weight" in params:
+                w = torch.cat([params[c + ".weight"], params[b + ".weight"]], 0).detach().float().contiguous()
+                bias = torch.cat([params[c + ".bias"], params[b + ".bias"]], 0).detach().float().contiguous()
+                cout, cin = w.shape[0], w.shape[1]
+                packed = torch.empty(cin, (cout + 3) // 4 * 4, dtype=torch.float32, device=w.device)
+                S.check(S.lib.sis3d_pack_conv_weight(S.ptr(w), cout, cin, 1, S.ptr(packed), S.stream()), "pack")
+                self._packed[f"rpn_heads_level{lvl}"] = (packed, bias, cout, cin, 1)
         torch.cuda.current_stream().synchronize()
         self._packed_version = v
 
@@ -218,14 +227,14 @@ class Network(nn.Module):
             regions, n_tiles = regions
         if out is None:
             out = Act(torch.empty(*out_dims, cout, dtype=torch.float32, device=x.t.device), out_dims, cout)
-        if (self._math == "tf32" and regions_given is None and name in self._packed_tc and stride == 1 and pad == 1
-                and x.layout == "vc" and x.ld == x.C and x.coff == 0 and act in (0, 1)):
+        if (self._math == "tf32" and regions_given is None and name in self._packed_tc and stride == 1
+                and pad == (1 if ks == 3 else 0) and x.layout == "vc" and x.ld == x.C and x.coff == 0 and act in (0, 1)):
             tok = self._rec(f"conv_tc[{name}]")
             S.check(S.lib.sis3d_conv3d_k3_tc(S.ptr(x.t), S.ptr(self._packed_tc[name]), S.ptr(bias),
                                              S.ptr(residual.t) if residual is not None else None,
                                              residual.ld if residual is not None else 0,
                                              residual.coff if residual is not None else 0,
-                                             S.ptr(out.t), out.ld, out.coff, *x.dims, cin, cout, None, 0, act, S.stream()),
+                                             S.ptr(out.t), out.ld, out.coff, *x.dims, cin, cout, ks, None, 0, act, S.stream()),
                     f"conv3d_k3_tc[{name}]")
             self._rec_end(tok)
             return out
@@ -387,17 +396,18 @@ class Network(nn.Module):
             if not A or f is None:
                 continue
             h = self._conv(f, f"rpn_net_level{lvl}", act=1)
-            cls = self._conv(h, f"rpn_cls_score_net_level{lvl}.0")
-            bbox = self._conv(h, f"rpn_bbox_pred_net_level{lvl}")
+            heads = self._conv(h, f"rpn_heads_level{lvl}")  # [N, 2A + 6A]
+            cls = Act(heads.t, f.dims, 2 * A, ld=8 * A, coff=0)
+            bbox = Act(heads.t.reshape(-1)[2 * A:], f.dims, 6 * A, ld=8 * A, coff=0)
             name = cfg["ANCHORS_TYPE_LEVEL%d" % lvl]
             sizes = self._const(("anchors", name, f.t.device), lambda: torch.tensor(
                 read_anchor_sizes(name), dtype=torch.float32, device=f.t.device).contiguous())
             if sizes.shape[0] != A:
                 raise S.Sis3dError(f"anchor table {name} has {sizes.shape[0]} rows, cfg says {A}")
-            levels.append(dict(cls=cls.t, deltas=bbox.t, sizes=sizes, grid=f.dims, A=A, cls_mode=0))
+            levels.append(dict(cls=cls.t, deltas=bbox.t, sizes=sizes, grid=f.dims, A=A, cls_mode=0, cls_ld=8 * A,
+                               deltas_ld=8 * A))
             if self._keep_debug:
-                self._predictions[f"rpn_cls_logits_level{lvl}"] = cls.t
-                self._predictions[f"rpn_bbox_pred_level{lvl}"] = bbox.t
+                self._predictions[f"rpn_heads_level{lvl}"] = heads.t  # [..., :2A] class logits, [..., 2A:] box deltas
         tok = self._rec("rpn_proposals")
         res = rpn_proposals(levels, dims, "TEST", want_order=self._keep_debug)
         self._rec_end(tok)
@@ -419,11 +429,18 @@ class Network(nn.Module):
                                             S.f32(1.0 / self._feat_stride[0]), R, *f1.dims, f1.C, P, P, P, S.ptr(rois),
                                             S.ptr(pool5), None, S.stream()), "roi_pool_levels")
         self._rec_end(tok)
-        x = pool5
-        for name, act in (("classifier.0", 1), ("classifier.2", 1), ("classifier.4", 1)):
-            x = self._linear(x, name, act)
-        cls_score = Act(self._linear(x, "classifier_cls_score_net", 0), (R, 1, 1), int(cfg.NUM_CLASSES))
-        bbox_pred = Act(self._linear(x, "classifier_bbox_pred_net", 0), (R, 1, 1), int(cfg.NUM_CLASSES) * 6)
+        x1 = self._linear(pool5, "classifier.0", 1)
+        nc = int(cfg.NUM_CLASSES)
+        cls_t = torch.empty(R, nc, dtype=torch.float32, device=dev)
+        box_t = torch.empty(R, nc * 6, dtype=torch.float32, device=dev)
+        p2, p3 = self._packed["classifier.2"], self._packed["classifier.4"]
+        pc, pb = self._packed["classifier_cls_score_net"], self._packed["classifier_bbox_pred_net"]
+        tok = self._rec("mlp_tail")
+        S.check(S.lib.sis3d_mlp_tail(S.ptr(x1), R, p2[3], S.ptr(p2[0]), S.ptr(p2[1]), p2[2], S.ptr(p3[0]), S.ptr(p3[1]), p3[2],
+                                     S.ptr(pc[0]), S.ptr(pc[1]), pc[2], S.ptr(pb[0]), S.ptr(pb[1]), pb[2], S.ptr(cls_t),
+                                     S.ptr(box_t), S.stream()), "mlp_tail")
+        self._rec_end(tok)
+        cls_score, bbox_pred = Act(cls_t, (R, 1, 1), nc), Act(box_t, (R, 1, 1), nc * 6)
         if self._keep_debug:
             self._predictions["pool5"] = pool5
         return cls_score.t.view(R, -1), bbox_pred.t.view(R, -1)
@@ -496,7 +513,7 @@ class Network(nn.Module):
                 dst = Act(bufs[(li + 1) % 2], (Xc, Yc, Zc), 64)
                 tok = self._rec(f"conv_tc[{name}]")
                 S.check(S.lib.sis3d_conv3d_k3_tc(S.ptr(x.t), S.ptr(self._packed_tc[name]), None, None, 0, 0, S.ptr(dst.t), 64,
-                                                 0, Xc, Yc, Zc, 64, 64, S.ptr(r_rest), tiles.shape[0], 1, S.stream()),
+                                                 0, Xc, Yc, Zc, 64, 64, 3, S.ptr(r_rest), tiles.shape[0], 1, S.stream()),
                         f"conv3d_k3_tc[{name}]")
                 self._rec_end(tok)
                 x = dst

@@ -140,20 +140,27 @@ size_t sis3d_linear_workspace_bytes(int M, int N, int K);
 int sis3d_linear(const float *x, const float *w_packed, const float *bias, float *y, int M, int K, int N,
                  int act, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Layers 2-3 of the classifier MLP and both heads in one launch (activations stay in shared memory):
+ * x1 [R][d1] -> relu(W2) [d2] -> relu(W3) [d3] -> cls_score [R][nc] and bbox_pred [R][nb].  All weights packed by
+ * sis3d_pack_conv_weight(ks=1); d1,d2,d3 <= 256.  (lib/nets/backbones.py:225-231, lib/nets/network.py:55-57) */
+int sis3d_mlp_tail(const float *x1, int R, int d1, const float *w2, const float *b2, int d2, const float *w3,
+                   const float *b3, int d3, const float *wc, const float *bc, int nc, const float *wb,
+                   const float *bb, int nb, float *cls_score, float *bbox_pred, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
- * Tensor-core path for the 3x3x3 / stride 1 / pad 1 layers (same call sites as sis3d_conv3d):
+ * Tensor-core path for the stride-1 layers, ks = 3 (pad 1) or ks = 1 (same call sites as sis3d_conv3d):
  * tcgen05.mma kind::tf32 with fp32 accumulation in TMEM, operands staged by 4-D/2-D TMA boxes
  * (csrc/conv_tc.cu).  `in` is a dense VC tensor [X][Y][Z][cin]; w_tc comes from
- * sis3d_pack_conv_weight_tc ([cout][27*cin]).  tiles == NULL covers the whole volume with 8x4x4
+ * sis3d_pack_conv_weight_tc ([cout][ks^3*cin]).  tiles == NULL covers the whole volume with 8x4x4
  * bricks; otherwise tiles int32[n_tiles][8] = {x0,y0,z0,x1,y1,z1,0,0} lists brick origins and the
  * exclusive end of the voxels to be written (ragged RoI crops packed on one canvas).
  * Requires cin % 32 == 0 and cout in {32, 64, 128k}; returns SIS3D_EUNSUPPORTED otherwise.
  * ---------------------------------------------------------------------------------------------- */
-int sis3d_pack_conv_weight_tc(const float *w_oidhw, int cout, int cin, float *w_tc, void *stream);
+int sis3d_pack_conv_weight_tc(const float *w_oidhw, int cout, int cin, int ks, float *w_tc, void *stream);
 int sis3d_conv3d_k3_tc_supported(int cin, int cout);
 int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const float *bias, const float *residual,
                        int res_ld, int res_coff, float *out, int out_ld, int out_coff, int X, int Y,
-                       int Z, int cin, int cout, const int32_t *tiles, int n_tiles, int act, void *stream);
+                       int Z, int cin, int cout, int ks, const int32_t *tiles, int n_tiles, int act, void *stream);
 
 /* MaxPool3d(3,1,1) on a VC tensor (lib/nets/backbones.py:207,212,220); output row stride out_ld and
  * channel offset out_coff as for the convolution. */
@@ -179,6 +186,8 @@ typedef struct sis3d_rpn_level {
     int32_t grid[3];
     int32_t num_anchors;
     int32_t cls_mode; /* 0: cls = logits [N][2A]; 1: cls = foreground probability [N][A] */
+    int32_t cls_ld;    /* row stride of cls in elements (0 = dense) -- lets both heads share one conv output */
+    int32_t deltas_ld; /* row stride of deltas in elements (0 = dense 6A) */
     int32_t pad_;
 } sis3d_rpn_level;
 size_t sis3d_rpn_workspace_bytes(const sis3d_rpn_level *h_levels, int n_levels, int pre_top_n);

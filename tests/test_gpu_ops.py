@@ -344,32 +344,34 @@ def test_rpn_proposals_few_candidates(oracle):
 
 
 # ---------------------------------------------------------------- tensor-core 3x3x3 conv (tcgen05, TF32)
-TC_CASES = [  # cin, cout, dims, bias, res, act
-    (32, 32, (8, 4, 4), True, False, 1), (32, 32, (17, 9, 11), True, False, 1), (64, 64, (24, 12, 24), True, False, 1),
-    (128, 128, (11, 6, 10), False, False, 1), (128, 256, (24, 12, 24), True, False, 1), (64, 64, (9, 5, 3), False, True, 0)]
+TC_CASES = [  # cin, cout, dims, bias, res, act, ks
+    (32, 32, (8, 4, 4), True, False, 1, 3), (32, 32, (17, 9, 11), True, False, 1, 3), (64, 64, (24, 12, 24), True, False, 1, 3),
+    (128, 128, (11, 6, 10), False, False, 1, 3), (128, 256, (24, 12, 24), True, False, 1, 3),
+    (64, 64, (9, 5, 3), False, True, 0, 3), (32, 32, (48, 24, 48), True, False, 1, 1), (64, 32, (11, 6, 9), True, False, 1, 1),
+    (32, 64, (24, 12, 24), True, True, 1, 1), (128, 64, (24, 12, 24), True, False, 1, 1), (64, 128, (7, 5, 6), True, True, 1, 1)]
 
 
-@pytest.mark.parametrize("cin,cout,dims,bias,res,act", TC_CASES)
-def test_conv3d_tc_tf32_vs_fp32(S, cin, cout, dims, bias, res, act):
+@pytest.mark.parametrize("cin,cout,dims,bias,res,act,ks", TC_CASES)
+def test_conv3d_tc_tf32_vs_fp32(S, cin, cout, dims, bias, res, act, ks):
     """tcgen05 kind::tf32 implicit GEMM vs torch fp32: TF32 operand rounding (10-bit mantissa) bounds the
     error at ~1e-3 relative; accumulation is fp32 in TMEM."""
     rng = np.random.default_rng(cin + cout + dims[0])
     x = rng.standard_normal((1, cin) + dims).astype(np.float32)
-    w = (rng.standard_normal((cout, cin, 3, 3, 3)) / np.sqrt(cin * 27)).astype(np.float32)
+    w = (rng.standard_normal((cout, cin, ks, ks, ks)) / np.sqrt(cin * ks ** 3)).astype(np.float32)
     b = rng.standard_normal(cout).astype(np.float32) if bias else None
-    ref = F.conv3d(torch.from_numpy(x), torch.from_numpy(w), None if b is None else torch.from_numpy(b), padding=1)
+    ref = F.conv3d(torch.from_numpy(x), torch.from_numpy(w), None if b is None else torch.from_numpy(b), padding=ks // 2)
     r = rng.standard_normal(tuple(ref.shape)).astype(np.float32) if res else None
     if res:
         ref = ref + torch.from_numpy(r)
     if act == 1:
         ref = F.relu(ref)
     xd = torch.from_numpy(x[0]).to(DEV).permute(1, 2, 3, 0).contiguous()
-    wtc = torch.empty(cout, 27 * cin, device=DEV)
-    S.check(S.lib.sis3d_pack_conv_weight_tc(S.ptr(torch.from_numpy(w).to(DEV)), cout, cin, S.ptr(wtc), S.stream()))
+    wtc = torch.empty(cout, ks ** 3 * cin, device=DEV)
+    S.check(S.lib.sis3d_pack_conv_weight_tc(S.ptr(torch.from_numpy(w).to(DEV)), cout, cin, ks, S.ptr(wtc), S.stream()))
     out = torch.full(dims + (cout + 4,), 7.0, device=DEV)
     rd = torch.from_numpy(r[0]).to(DEV).permute(1, 2, 3, 0).contiguous() if res else None
     S.check(S.lib.sis3d_conv3d_k3_tc(S.ptr(xd), S.ptr(wtc), S.ptr(torch.from_numpy(b).to(DEV)) if bias else None, S.ptr(rd),
-                                     cout if res else 0, 0, S.ptr(out), cout + 4, 4, *dims, cin, cout, None, 0, act, S.stream()))
+                                     cout if res else 0, 0, S.ptr(out), cout + 4, 4, *dims, cin, cout, ks, None, 0, act, S.stream()))
     torch.cuda.synchronize()
     got = out[..., 4:].permute(3, 0, 1, 2).cpu()
     assert torch.all(out[..., :4] == 7.0)
@@ -400,10 +402,10 @@ def test_conv3d_tc_tile_list(S):
                     tiles.append([x0 + bx, by, bz, x0 + s[0], s[1], s[2], 0, 0])
     td = torch.tensor(tiles, dtype=torch.int32, device=DEV)
     wtc = torch.empty(cout, 27 * cin, device=DEV)
-    S.check(S.lib.sis3d_pack_conv_weight_tc(S.ptr(torch.from_numpy(w).to(DEV)), cout, cin, S.ptr(wtc), S.stream()))
+    S.check(S.lib.sis3d_pack_conv_weight_tc(S.ptr(torch.from_numpy(w).to(DEV)), cout, cin, 3, S.ptr(wtc), S.stream()))
     out = torch.zeros(Xc, Yc, Zc, cout, device=DEV)
     S.check(S.lib.sis3d_conv3d_k3_tc(S.ptr(canvas.to(DEV)), S.ptr(wtc), None, None, 0, 0, S.ptr(out), cout, 0, Xc, Yc, Zc, cin,
-                                     cout, S.ptr(td), len(tiles), 1, S.stream()))
+                                     cout, 3, S.ptr(td), len(tiles), 1, S.stream()))
     torch.cuda.synchronize()
     for (x0, c), s in zip(crops, sizes):
         ref = F.relu(F.conv3d(c.permute(3, 0, 1, 2).unsqueeze(0), torch.from_numpy(w), padding=1))[0]
