@@ -14,3 +14,105 @@ extern "C" const char *sis3d_strerror(int code) {
 }
 extern "C" int sis3d_version(void) { return 100; }
 extern "C" int64_t sis3d_launch_count(void) { return (int64_t)sis3d::g_launch_count; }
+
+// ---- host-side planner of the ragged mask stage (pure CPU code: the "runtime" part of the per-RoI mask head) ------
+// From the decoded detection table it lays out, in one byte blob that the caller ships with a single pinned H2D copy:
+// region tables of the first (windowed NCDHW scene -> canvas/compact) and last (-> dense per-crop output) layers, the
+// 8x4x4 brick list of the tensor-core layers (canvas mode) or the region table of the middle layers (compact mode), voxel
+// offsets, predicted classes, kept row indices and crop sizes.  Mirrors lib/nets/network.py:296-311 (crop selection).
+extern "C" int sis3d_mask_plan_build(const float *h_det, int n, int X, int Y, int Z, int ncls, int use_canvas, void *h_blob,
+                                     size_t capacity, sis3d_mask_plan *plan) {
+    if (!h_det || !plan || n < 0) return SIS3D_EINVAL;
+    sis3d_mask_plan p = {};
+    int kept[4096];
+    for (int i = 0; i < n && p.n_kept < 4096; ++i)
+        if (h_det[i * 16 + 8] > 0.5f) kept[p.n_kept++] = i;
+    const int nk = p.n_kept;
+    if (nk == 0) { *plan = p; return SIS3D_OK; }
+    // pass 1: sizes
+    int64_t total = 0, xsum = 0;
+    int ymax = 0, zmax = 0;
+    int64_t ntiles = 0, t_mid = 0;
+    for (int j = 0; j < nk; ++j) {
+        const float *d = h_det + kept[j] * 16;
+        const int w = (int)d[12] - (int)d[9], h = (int)d[13] - (int)d[10], l = (int)d[14] - (int)d[11];
+        total += (int64_t)w * h * l;
+        xsum += w + 1;
+        ymax = h > ymax ? h : ymax;
+        zmax = l > zmax ? l : zmax;
+        ntiles += (int64_t)((w + 7) / 8) * ((h + 3) / 4) * ((l + 3) / 4);
+        t_mid += ((int64_t)w * h * l + SIS3D_CONV_TILE_M - 1) / SIS3D_CONV_TILE_M;
+    }
+    p.total_voxels = total;
+    p.canvas[0] = (int)xsum; p.canvas[1] = ymax; p.canvas[2] = zmax;
+    p.n_tiles_tc = use_canvas ? (int)ntiles : 0;
+    const size_t rb = sizeof(sis3d_region) * (size_t)nk;
+    p.off_first = 0;
+    p.off_last = rb;
+    p.off_rest = 2 * rb;
+    const size_t rest = use_canvas ? (size_t)ntiles * 32 : rb;
+    p.off_offs = (p.off_rest + rest + 7) & ~(size_t)7;
+    p.off_cls = p.off_offs + 8 * (size_t)(nk + 1);
+    p.off_kept = p.off_cls + 4 * (size_t)nk;
+    p.off_sizes = p.off_kept + 4 * (size_t)nk;
+    p.bytes = p.off_sizes + 12 * (size_t)nk;
+    if (!h_blob || capacity < (size_t)p.bytes) { *plan = p; return SIS3D_EWORKSPACE; }
+    char *blob = (char *)h_blob;
+    sis3d_region *first = (sis3d_region *)(blob + p.off_first), *last = (sis3d_region *)(blob + p.off_last);
+    sis3d_region *mid = (sis3d_region *)(blob + p.off_rest);
+    int32_t *tiles = (int32_t *)(blob + p.off_rest);
+    int64_t *offs = (int64_t *)(blob + p.off_offs);
+    int32_t *cls = (int32_t *)(blob + p.off_cls), *kidx = (int32_t *)(blob + p.off_kept), *sizes = (int32_t *)(blob + p.off_sizes);
+    const int64_t cs0 = (int64_t)ymax * zmax * 64, cs1 = (int64_t)zmax * 64, cs2 = 64;
+    int64_t voff = 0, xoff = 0, tile_no = 0;
+    int tb = 0;
+    for (int j = 0; j < nk; ++j) {
+        const float *d = h_det + kept[j] * 16;
+        const int x0 = (int)d[9], y0 = (int)d[10], z0 = (int)d[11];
+        const int w = (int)d[12] - x0, h = (int)d[13] - y0, l = (int)d[14] - z0;
+        const int64_t vox = (int64_t)w * h * l;
+        const int tl = (int)((vox + SIS3D_CONV_TILE_M - 1) / SIS3D_CONV_TILE_M);
+        sis3d_region f = {}, q = {};
+        f.in_off = ((int64_t)x0 * Y + y0) * Z + z0;
+        f.in_dim[0] = f.out_dim[0] = w; f.in_dim[1] = f.out_dim[1] = h; f.in_dim[2] = f.out_dim[2] = l;
+        f.in_stride[0] = (int64_t)Y * Z; f.in_stride[1] = Z; f.in_stride[2] = 1;
+        f.tile_begin = tb;
+        q.in_dim[0] = q.out_dim[0] = w; q.in_dim[1] = q.out_dim[1] = h; q.in_dim[2] = q.out_dim[2] = l;
+        q.out_off = voff * ncls;
+        q.tile_begin = tb;
+        if (use_canvas) {
+            f.out_off = xoff * cs0;
+            f.out_stride[0] = cs0; f.out_stride[1] = cs1; f.out_stride[2] = cs2;
+            q.in_off = xoff * cs0;
+            q.in_stride[0] = cs0; q.in_stride[1] = cs1; q.in_stride[2] = cs2;
+            for (int bx = 0; bx < w; bx += 8)
+                for (int by = 0; by < h; by += 4)
+                    for (int bz = 0; bz < l; bz += 4) {
+                        int32_t *t = tiles + tile_no * 8;
+                        t[0] = (int32_t)xoff + bx; t[1] = by; t[2] = bz;
+                        t[3] = (int32_t)xoff + w; t[4] = h; t[5] = l; t[6] = t[7] = 0;
+                        ++tile_no;
+                    }
+        } else {
+            f.out_off = voff * 64;
+            q.in_off = voff * 64;
+            q.in_stride[0] = (int64_t)h * l * 64; q.in_stride[1] = (int64_t)l * 64; q.in_stride[2] = 64;
+            sis3d_region m = q;
+            m.out_off = voff * 64;
+            mid[j] = m;
+        }
+        first[j] = f;
+        last[j] = q;
+        offs[j] = voff;
+        cls[j] = (int32_t)d[7];
+        kidx[j] = kept[j];
+        sizes[3 * j] = w; sizes[3 * j + 1] = h; sizes[3 * j + 2] = l;
+        voff += vox;
+        xoff += w + 1;
+        tb += tl;
+    }
+    offs[nk] = voff;
+    p.tiles_first = p.tiles_last = p.tiles_mid = tb;
+    *plan = p;
+    return SIS3D_OK;
+}

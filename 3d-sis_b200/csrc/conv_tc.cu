@@ -25,7 +25,7 @@ namespace sis3d {
 constexpr int TC_BX = 8, TC_BY = 4, TC_BZ = 4;
 constexpr int TC_BM = TC_BX * TC_BY * TC_BZ;  // 128
 constexpr int TC_KC = 32;                      // channels per stage: 32 * 4 B = 128 B = one swizzle row
-constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES_MAX = 4;
 constexpr int TC_A_BYTES = TC_BM * 128;
 
 struct TcArgs {
@@ -102,11 +102,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// stages: 4 for BN = 128 (128 KB), 3 for BN <= 64 so that three CTAs fit one SM (the grids of the narrow layers are
+// ~1.3-1.5 waves at two CTAs/SM)
+template <int BN>
+struct TcStages { static constexpr int value = BN >= 128 ? 4 : 3; };
+
 template <int BN, int KS>
 __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
     constexpr int B_BYTES = BN * 128;
     constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+    constexpr int TC_STAGES = TcStages<BN>::value;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B needs 1024 B alignment
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + TC_STAGES * STAGE_BYTES);
@@ -241,7 +247,7 @@ static EncodeTiledFn get_encode() {
 
 template <int BN, int KS>
 static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcArgs &a, int n_tiles, cudaStream_t s) {
-    const size_t smem = (size_t)TC_STAGES * (TC_A_BYTES + BN * 128) + 1024 + 256;
+    const size_t smem = (size_t)TcStages<BN>::value * (TC_A_BYTES + BN * 128) + 1024 + 256;
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(conv3d_k3_tc_kernel<BN, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)

@@ -63,64 +63,46 @@ __global__ void __launch_bounds__(256) roi_pool_ncdhw_kernel(int nthreads, const
     }
 }
 
-constexpr int kRoiMaxBins = 64;
-// grid = RoIs, block = 128 threads (channels); smem staging so the [C][bins] rows are written coalesced
+// grid = (RoIs, pw*ph); block = 128 threads (channels).  Each CTA pools the pl bins of one (pw, ph) column, so a
+// large RoI is spread over pw*ph CTAs instead of serialising 64 bins in one.
 __global__ void __launch_bounds__(128) roi_pool_vc_kernel(const float *feat1, const float *feat2, const float *feat3,
                                                           const int32_t *level_ids, float scale, int W, int H, int L, int C,
                                                           int pw_, int ph_, int pl_, const float *rois, float *top, int *argmax) {
-    extern __shared__ float s_out[];  // [blockDim.x][nb+1] values, then ints for argmax
     const int r = blockIdx.x;
+    const int pw = blockIdx.y / ph_, ph = blockIdx.y % ph_;
     const int nb = pw_ * ph_ * pl_;
-    int *s_arg = reinterpret_cast<int *>(s_out + blockDim.x * (nb + 1));
     const int lvl = level_ids ? level_ids[r] : 1;
     const float *feat = lvl == 1 ? feat1 : (lvl == 2 ? feat2 : (lvl == 3 ? feat3 : nullptr));
     const RoiBins b = roi_bins(rois + r * 6, scale, pw_, ph_, pl_);
-    for (int c0 = 0; c0 < C; c0 += blockDim.x) {
-        const int c = c0 + threadIdx.x;
-        if (c < C) {
-            int bin = 0;
-            for (int pw = 0; pw < pw_; ++pw) {
-                int ws, we;
-                bin_range(pw, b.bw, b.sw, W, ws, we);
-                for (int ph = 0; ph < ph_; ++ph) {
-                    int hs, he;
-                    bin_range(ph, b.bh, b.sh, H, hs, he);
-                    for (int pl = 0; pl < pl_; ++pl, ++bin) {
-                        int ls, le;
-                        bin_range(pl, b.bl, b.sl, L, ls, le);
-                        const bool empty = (he <= hs) || (we <= ws) || (le <= ls) || !feat;
-                        float best = empty ? 0.f : -FLT_MAX;
-                        int besti = -1;
-                        if (!empty)
-                            for (int w = ws; w < we; ++w)
-                                for (int h = hs; h < he; ++h) {
-                                    const float *row = feat + ((int64_t)(w * H + h) * L) * C + c;
-                                    for (int l = ls; l < le; ++l) {
-                                        const float v = __ldg(row + (int64_t)l * C);
-                                        if (v > best) { best = v; besti = (c * W + w) * H * L + h * L + l; }
-                                    }
-                                }
-                        s_out[threadIdx.x * (nb + 1) + bin] = best;
-                        s_arg[threadIdx.x * (nb + 1) + bin] = besti;
+    int ws, we, hs, he;
+    bin_range(pw, b.bw, b.sw, W, ws, we);
+    bin_range(ph, b.bh, b.sh, H, hs, he);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        for (int pl = 0; pl < pl_; ++pl) {
+            int ls, le;
+            bin_range(pl, b.bl, b.sl, L, ls, le);
+            const bool empty = (he <= hs) || (we <= ws) || (le <= ls) || !feat;
+            float best = empty ? 0.f : -FLT_MAX;
+            int besti = -1;
+            if (!empty)
+                for (int w = ws; w < we; ++w)
+                    for (int h = hs; h < he; ++h) {
+                        const float *row = feat + ((int64_t)(w * H + h) * L) * C + c;
+                        for (int l = ls; l < le; ++l) {
+                            const float v = __ldg(row + (int64_t)l * C);
+                            if (v > best) { best = v; besti = (c * W + w) * H * L + h * L + l; }
+                        }
                     }
-                }
-            }
+            const int64_t o = ((int64_t)r * C + c) * nb + (pw * ph_ + ph) * pl_ + pl;
+            top[o] = best;
+            if (argmax) argmax[o] = besti;
         }
-        __syncthreads();
-        const int cn = min((int)blockDim.x, C - c0);
-        for (int i = threadIdx.x; i < cn * nb; i += blockDim.x) {
-            const int cc = i / nb, bb = i - cc * nb;
-            const int64_t o = ((int64_t)r * C + c0 + cc) * nb + bb;
-            top[o] = s_out[cc * (nb + 1) + bb];
-            if (argmax) argmax[o] = s_arg[cc * (nb + 1) + bb];
-        }
-        __syncthreads();
     }
 }
 
 // Tail of the RoI classifier (lib/nets/backbones.py:225-231 layers 2,4 + lib/nets/network.py:55-57 heads) in one
 // launch: 8 RoI rows per CTA, activations stay in shared memory, weights ([K][ldw] packed) stream from L2.
-constexpr int kMlpRows = 8;
+constexpr int kMlpRows = 4;
 __global__ void __launch_bounds__(256) mlp_tail_kernel(const float *x1, int R, int d1, const float *w2, const float *b2, int d2,
                                                        const float *w3, const float *b3, int d3, const float *wc,
                                                        const float *bc, int nc, const float *wb, const float *bb, int nb,
@@ -138,6 +120,7 @@ __global__ void __launch_bounds__(256) mlp_tail_kernel(const float *x1, int R, i
 #pragma unroll
         for (int r = 0; r < kMlpRows; ++r) acc[r] = 0.f;
         const int ld = (d2 + 3) & ~3;
+#pragma unroll 8
         for (int k = 0; k < d1; ++k) {
             const float w = __ldg(w2 + (int64_t)k * ld + t);
 #pragma unroll
@@ -151,6 +134,7 @@ __global__ void __launch_bounds__(256) mlp_tail_kernel(const float *x1, int R, i
 #pragma unroll
         for (int r = 0; r < kMlpRows; ++r) acc[r] = 0.f;
         const int ld = (d3 + 3) & ~3;
+#pragma unroll 8
         for (int k = 0; k < d2; ++k) {
             const float w = __ldg(w3 + (int64_t)k * ld + t);
 #pragma unroll
@@ -167,6 +151,7 @@ __global__ void __launch_bounds__(256) mlp_tail_kernel(const float *x1, int R, i
         const int ld = ((is_cls ? nc : nb) + 3) & ~3;
 #pragma unroll
         for (int r = 0; r < kMlpRows; ++r) acc[r] = 0.f;
+#pragma unroll 8
         for (int k = 0; k < d3; ++k) {
             const float wv = __ldg(w + (int64_t)k * ld + n);
 #pragma unroll
@@ -179,6 +164,24 @@ __global__ void __launch_bounds__(256) mlp_tail_kernel(const float *x1, int R, i
     }
 }
 
+// Predicted-class channel of every kept RoI's mask, packed back to back (what the driver saves:
+// lib/model/trainval.py:900-908).  masks [total][ncls] (crop j occupies rows offs[j]..offs[j+1]); out float [total],
+// bits uint8 [total] = (value >= thresh).
+__global__ void mask_select_kernel(const float *masks, const int64_t *offs, const int32_t *cls, int n_crops, int ncls,
+                                   float thresh, float *out, uint8_t *bits) {
+    const int64_t total = offs[n_crops];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int lo = 0, hi = n_crops - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (offs[mid] <= i) lo = mid; else hi = mid - 1;
+        }
+        const float v = masks[i * ncls + cls[lo]];
+        if (out) out[i] = v;
+        if (bits) bits[i] = v >= thresh ? 1 : 0;
+    }
+}
+
 // one thread per RoI row
 __global__ void detect_decode_kernel(const float *rois, const int32_t *num_rois, int max_rois, const float *cls_score,
                                      const float *bbox_pred, int nc, int sx, int sy, int sz, float thresh, float *cls_prob,
@@ -187,8 +190,10 @@ __global__ void detect_decode_kernel(const float *rois, const int32_t *num_rois,
     if (i >= max_rois) return;
     const int n = min(*num_rois, max_rois);
     float *d = det + i * 16;
+    const float tag = i == 0 ? (float)n : 0.f;  // row 0, column 15 carries the RoI count (one D2H for count + table)
     if (i >= n) {
-        for (int k = 0; k < 16; ++k) d[k] = 0.f;
+        for (int k = 0; k < 15; ++k) d[k] = 0.f;
+        d[15] = tag;
         cls_pred[i] = 0;
         for (int k = 0; k < nc; ++k) cls_prob[i * nc + k] = 0.f;
         return;
@@ -225,7 +230,7 @@ __global__ void detect_decode_kernel(const float *rois, const int32_t *num_rois,
     for (int k = 0; k < 6; ++k) d[k] = box[k];
     d[6] = conf; d[7] = (float)best; d[8] = keep ? 1.f : 0.f;
     for (int k = 0; k < 6; ++k) d[9 + k] = crop[k];
-    d[15] = 0.f;
+    d[15] = tag;
 }
 
 }  // namespace sis3d
@@ -243,12 +248,8 @@ extern "C" int sis3d_roi_pool_fwd(const float *feat, int feat_layout, float spat
                                                                                 length, channels, pw, ph, pl, rois, top,
                                                                                 argmax);
     } else {
-        const int nb = pw * ph * pl;
-        const size_t smem = (size_t)128 * (nb + 1) * 8;
-        if (smem > 200 * 1024) return SIS3D_EUNSUPPORTED;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(roi_pool_vc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        roi_pool_vc_kernel<<<num_rois, 128, smem, s>>>(feat, nullptr, nullptr, nullptr, spatial_scale, width, height, length,
-                                                     channels, pw, ph, pl, rois, top, argmax);
+        roi_pool_vc_kernel<<<dim3(num_rois, pw * ph), 128, 0, s>>>(feat, nullptr, nullptr, nullptr, spatial_scale, width, height,
+                                                                  length, channels, pw, ph, pl, rois, top, argmax);
     }
     return finish_launch();
 }
@@ -257,12 +258,9 @@ extern "C" int sis3d_roi_pool_levels(const float *feat1, const float *feat2, con
                                      float spatial_scale, int num_rois, int width, int height, int length, int channels,
                                      int pw, int ph, int pl, const float *rois, float *top, int32_t *argmax, void *stream) {
     if (!feat1 || !level_ids || !rois || !top || num_rois <= 0) return SIS3D_EINVAL;
-    const int nb = pw * ph * pl;
-    const size_t smem = (size_t)128 * (nb + 1) * 8;
-    if (smem > 200 * 1024) return SIS3D_EUNSUPPORTED;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(roi_pool_vc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    roi_pool_vc_kernel<<<num_rois, 128, smem, (cudaStream_t)stream>>>(feat1, feat2, feat3, level_ids, spatial_scale, width,
-                                                                    height, length, channels, pw, ph, pl, rois, top, argmax);
+    roi_pool_vc_kernel<<<dim3(num_rois, pw * ph), 128, 0, (cudaStream_t)stream>>>(feat1, feat2, feat3, level_ids, spatial_scale,
+                                                                                 width, height, length, channels, pw, ph, pl,
+                                                                                 rois, top, argmax);
     return finish_launch();
 }
 
@@ -283,5 +281,13 @@ extern "C" int sis3d_mlp_tail(const float *x1, int R, int d1, const float *w2, c
     if (d1 > 256 || d2 > 256 || d3 > 256 || d1 <= 0 || d2 <= 0 || d3 <= 0 || nc <= 0 || nb <= 0) return SIS3D_EUNSUPPORTED;
     mlp_tail_kernel<<<cdiv(R, kMlpRows), 256, 0, (cudaStream_t)stream>>>(x1, R, d1, w2, b2, d2, w3, b3, d3, wc, bc, nc, wb, bb, nb,
                                                                         cls_score, bbox_pred);
+    return finish_launch();
+}
+
+extern "C" int sis3d_mask_select(const float *masks, const int64_t *offs, const int32_t *cls, int n_crops, int ncls,
+                                 int64_t total_hint, float thresh, float *out, uint8_t *bits, void *stream) {
+    if (!masks || !offs || !cls || n_crops <= 0 || ncls <= 0 || (!out && !bits)) return SIS3D_EINVAL;
+    const int blocks = (int)imin64(cdiv64(total_hint > 0 ? total_hint : 1, 256), kNumSMs * 8);
+    mask_select_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(masks, offs, cls, n_crops, ncls, thresh, out, bits);
     return finish_launch();
 }

@@ -163,8 +163,10 @@ __global__ void __launch_bounds__(256) sparse_combine_kernel(const SparseArgs a,
     }
 }
 
-__global__ void feats_transpose_kernel2(const float *in, float *out, int C, int hw) {
+__global__ void feats_transpose_kernel2(const float *in, float *out, int C, int hw, int32_t *zero8) {
     __shared__ float tile[32][33];
+    if (zero8 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.y == 0 && threadIdx.x < 8)
+        zero8[threadIdx.x] = 0;  // per-tap counters of the cover pass (saves a memset node)
     const float *src = in + (int64_t)blockIdx.z * C * hw;
     float *dst = out + (int64_t)blockIdx.z * C * hw;
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -213,9 +215,8 @@ extern "C" int sis3d_backproject_conv_k2s2(const float *feats, float *feats_t, c
     a.feats_t = feats_t; a.pix = pix; a.pairs = pairs; a.n_pairs = n_pairs;
     a.C = C; a.hw = img_w * img_h; a.X = X; a.Y = Y; a.Z = Z; a.n_views = n_views; a.n0 = (int64_t)X * Y * Z;
     cudaStream_t s = (cudaStream_t)stream;
-    if (cudaMemsetAsync(a.counts, 0, 64, s) != cudaSuccess) return SIS3D_ELAUNCH;
     dim3 tg(cdiv(a.hw, 32), cdiv(C, 32), n_views);
-    feats_transpose_kernel2<<<tg, dim3(32, 8), 0, s>>>(feats, feats_t, C, a.hw);
+    feats_transpose_kernel2<<<tg, dim3(32, 8), 0, s>>>(feats, feats_t, C, a.hw, a.counts);
     sparse_cover_kernel<<<(int)imin64(cdiv64(a.n0, 256), kNumSMs * 8), 256, 0, s>>>(a);
     const size_t smem = sizeof(float) * ((size_t)C * (SP_BM + 4) + (size_t)C * cout);
     if (smem > 200 * 1024) return SIS3D_EUNSUPPORTED;

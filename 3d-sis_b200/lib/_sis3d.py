@@ -39,6 +39,14 @@ class RpnLevel(C.Structure):
                 ("deltas_ld", C.c_int32), ("pad_", C.c_int32)]
 
 
+class MaskPlan(C.Structure):
+    """struct sis3d_mask_plan (include/sis3d.h)."""
+    _fields_ = [("n_kept", C.c_int32), ("canvas", C.c_int32 * 3), ("n_tiles_tc", C.c_int32), ("tiles_first", C.c_int32),
+                ("tiles_last", C.c_int32), ("tiles_mid", C.c_int32), ("total_voxels", C.c_int64), ("off_first", C.c_int64),
+                ("off_last", C.c_int64), ("off_rest", C.c_int64), ("off_offs", C.c_int64), ("off_cls", C.c_int64),
+                ("off_kept", C.c_int64), ("off_sizes", C.c_int64), ("bytes", C.c_int64)]
+
+
 REGION_BYTES = C.sizeof(Region)
 TILE_M = 64
 
@@ -49,7 +57,7 @@ SYMBOLS = ["sis3d_strerror", "sis3d_version", "sis3d_launch_count", "sis3d_nms_w
            "sis3d_backproject_max", "sis3d_backproject_conv_k2s2_workspace_bytes", "sis3d_backproject_conv_k2s2",
            "sis3d_pack_conv_weight", "sis3d_conv3d", "sis3d_maxpool3",
            "sis3d_vc_to_ncdhw", "sis3d_linear_workspace_bytes", "sis3d_linear", "sis3d_mlp_tail", "sis3d_pack_conv_weight_tc", "sis3d_conv3d_k3_tc_supported", "sis3d_conv3d_k3_tc",
-           "sis3d_rpn_workspace_bytes", "sis3d_rpn_proposals", "sis3d_detect_decode"]
+           "sis3d_rpn_workspace_bytes", "sis3d_rpn_proposals", "sis3d_detect_decode", "sis3d_mask_plan_build", "sis3d_mask_select"]
 
 lib.sis3d_strerror.restype = C.c_char_p
 lib.sis3d_launch_count.restype = C.c_int64

@@ -13,7 +13,7 @@ from lib import _sis3d as S
 from lib.utils.config import cfg
 
 
-def rpn_proposals(levels, scene_dims, cfg_key="TEST", want_order=False):
+def rpn_proposals(levels, scene_dims, cfg_key="TEST", want_order=False, out=None):
     """levels: list of dict(cls, deltas, sizes [A,3] cuda f32, grid (gx,gy,gz), A, cls_mode).
     Returns rois [post,6], scores [post], level_ids int32 [post], num int32 [1] (+ order int32 [pre])."""
     pre, post = int(cfg[cfg_key].RPN_PRE_NMS_TOP_N), int(cfg[cfg_key].RPN_POST_NMS_TOP_N)
@@ -31,10 +31,13 @@ def rpn_proposals(levels, scene_dims, cfg_key="TEST", want_order=False):
         arr[i].cls_ld, arr[i].deltas_ld = int(lv.get("cls_ld", 0)), int(lv.get("deltas_ld", 0))
     nbytes = int(S.lib.sis3d_rpn_workspace_bytes(arr, len(levels), pre))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    rois = torch.empty(post, 6, dtype=torch.float32, device=dev)
-    scores = torch.empty(post, dtype=torch.float32, device=dev)
-    lvl = torch.empty(post, dtype=torch.int32, device=dev)
-    num = torch.empty(1, dtype=torch.int32, device=dev)
+    if out is not None:  # caller-provided outputs (views of one packed result buffer)
+        rois, scores, lvl, num = out
+    else:
+        rois = torch.empty(post, 6, dtype=torch.float32, device=dev)
+        scores = torch.empty(post, dtype=torch.float32, device=dev)
+        lvl = torch.empty(post, dtype=torch.int32, device=dev)
+        num = torch.empty(1, dtype=torch.int32, device=dev)
     order = torch.empty(pre, dtype=torch.int32, device=dev) if want_order else None
     S.check(S.lib.sis3d_rpn_proposals(arr, len(levels), 4, int(scene_dims[0]), int(scene_dims[1]), int(scene_dims[2]),
                                       int(cfg.ALLOW_BORDER), pre, post, S.f32(thresh), S.ptr(rois), S.ptr(scores),

@@ -41,9 +41,11 @@ def save_scene_results(out_dir, scene_id, blobs, net):
     np.save(os.path.join(d, "scene"), np.where(blobs["data"][0, 0].numpy() <= 1, 1, 0))
     if cfg.USE_MASK:
         masks = []
-        for m, cls in zip(net._predictions["mask_pred"][0], pred_class[keep]):
-            mm = m[0, int(cls)].cpu().numpy()
-            masks.append(np.where(mm >= cfg.MASK_THRESH, 1, 0).astype(np.float32))
+        if keep.any():  # one D2H of the thresholded predicted-class channels (csrc/roi.cu mask_select_kernel)
+            bits = net._predictions["mask_bits"].cpu().numpy()
+            offs, sizes = net._predictions["mask_offsets"], net._predictions["mask_sizes"]
+            for j in range(len(sizes)):
+                masks.append(bits[int(offs[j]):int(offs[j + 1])].reshape(tuple(int(v) for v in sizes[j])).astype(np.float32))
         with open(os.path.join(d, "pred_mask"), "wb") as f:
             pickle.dump(masks, f)
         with open(os.path.join(d, "pred_mask_index"), "wb") as f:

@@ -388,7 +388,7 @@ class Network(nn.Module):
         level2 = self._run_stack(level1, "geometry2", spec["geometry2"])
         return level1, level2
 
-    def _region_proposal(self, feats, dims):
+    def _region_proposal(self, feats, dims, out=None):
         """reference: network.py:537-587 + 657-683 (softmax/anchors/decode/top-N/NMS fused on device)."""
         levels = []
         for lvl, f in enumerate(feats, 1):
@@ -409,13 +409,13 @@ class Network(nn.Module):
             if self._keep_debug:
                 self._predictions[f"rpn_heads_level{lvl}"] = heads.t  # [..., :2A] class logits, [..., 2A:] box deltas
         tok = self._rec("rpn_proposals")
-        res = rpn_proposals(levels, dims, "TEST", want_order=self._keep_debug)
+        res = rpn_proposals(levels, dims, "TEST", want_order=self._keep_debug, out=out)
         self._rec_end(tok)
         if self._keep_debug:
             self._predictions["rpn_order"] = res[4]
         return res[:4]
 
-    def _classify(self, feats, rois, level_ids):
+    def _classify(self, feats, rois, level_ids, out=None):
         """RoI pooling per pyramid level + MLP + heads (reference: network.py:503-534, backbones.py:92-96,
         network.py:589-604).  Always processes the padded post-NMS row count; rows >= num are zeros."""
         P = int(cfg.CLASS_POOLING_SIZE)
@@ -431,8 +431,11 @@ class Network(nn.Module):
         self._rec_end(tok)
         x1 = self._linear(pool5, "classifier.0", 1)
         nc = int(cfg.NUM_CLASSES)
-        cls_t = torch.empty(R, nc, dtype=torch.float32, device=dev)
-        box_t = torch.empty(R, nc * 6, dtype=torch.float32, device=dev)
+        if out is not None:
+            cls_t, box_t = out
+        else:
+            cls_t = torch.empty(R, nc, dtype=torch.float32, device=dev)
+            box_t = torch.empty(R, nc * 6, dtype=torch.float32, device=dev)
         p2, p3 = self._packed["classifier.2"], self._packed["classifier.4"]
         pc, pb = self._packed["classifier_cls_score_net"], self._packed["classifier_bbox_pred_net"]
         tok = self._rec("mlp_tail")
@@ -450,58 +453,44 @@ class Network(nn.Module):
         one zeroed canvas [sum(w_j + 1), max h, max l, 64] (one zero slab between crops = the crop-border
         zero padding), so each of the six layers is ONE launch: layer 1 (C_in = 2, windowed NCDHW scene) and
         the 1x1 head on the fp32 CUDA-core kernel, the four 64->64 3x3x3 layers on the tcgen05 kernel driven
-        by an explicit list of 8x4x4 bricks.  Tables are built vectorised on the host and shipped in ONE
-        pinned H2D copy; all buffers come from a grow-only arena."""
-        keep = np.nonzero(det_host[:n, 8] > 0.5)[0]
-        if keep.size == 0:
-            return []
+        by an explicit list of 8x4x4 bricks.  The tables come from the native planner (sis3d_mask_plan_build)
+        and travel in ONE pinned H2D copy; all buffers come from a grow-only arena."""
         dev = scene_ncdhw.device
         X, Y, Z = (int(v) for v in scene_ncdhw.shape[2:])
-        crops = det_host[keep, 9:15].astype(np.int64)
-        sizes = crops[:, 3:6] - crops[:, 0:3]
-        vox = sizes.prod(1)
-        offs = np.concatenate([[0], np.cumsum(vox)])
-        total = int(offs[-1])
-        nk = len(keep)
         ncls = self._packed["mask_backbone.geometry.10"][2]
+        use_tc = self._math == "tf32" and "mask_backbone.geometry.2" in self._packed_tc
+        det_host = np.ascontiguousarray(det_host[:n], dtype=np.float32)
+        plan = S.MaskPlan()
+        cap = self._arena["mask_tables_host"].numel() if "mask_tables_host" in self._arena else 1 << 18
+        while True:
+            stage = self._ws("mask_tables_host", cap, torch.uint8, dev, pinned=True)
+            rc = S.lib.sis3d_mask_plan_build(C.c_void_p(det_host.ctypes.data), n, X, Y, Z, ncls, 1 if use_tc else 0,
+                                             C.c_void_p(stage.data_ptr()), C.c_size_t(stage.numel()), C.byref(plan))
+            if rc == -3:  # SIS3D_EWORKSPACE: grow the pinned staging buffer and retry
+                cap = int(plan.bytes) * 2
+                continue
+            S.check(rc, "mask_plan_build")
+            break
+        nk = int(plan.n_kept)
+        if nk == 0:
+            return []
+        nbytes, total = int(plan.bytes), int(plan.total_voxels)
+        tables = self._ws("mask_tables", nbytes, torch.uint8, dev)
+        tables.copy_(stage[:nbytes], non_blocking=True)
+        host = stage.numpy()
+        offs = host[plan.off_offs:plan.off_offs + 8 * (nk + 1)].view(np.int64).copy()
+        sizes = host[plan.off_sizes:plan.off_sizes + 12 * nk].view(np.int32).reshape(nk, 3).copy()
+        rb = nk * S.REGION_BYTES
+        r_first, r_last = tables[plan.off_first:plan.off_first + rb], tables[plan.off_last:plan.off_last + rb]
+        d_offs = tables[plan.off_offs:plan.off_offs + 8 * (nk + 1)]
+        d_cls = tables[plan.off_cls:plan.off_cls + 4 * nk]
+        t_first, t_last = int(plan.tiles_first), int(plan.tiles_last)
         outb = torch.empty(total * ncls, dtype=torch.float32, device=dev)  # handed to the caller (mask_pred views)
         scene = Act(scene_ncdhw, (X, Y, Z), 2, layout="ncdhw")
-        scene_off = (crops[:, 0] * Y + crops[:, 1]) * Z + crops[:, 2]
-        scene_str = np.tile(np.array([Y * Z, Z, 1], dtype=np.int64), (nk, 1))
-        use_tc = self._math == "tf32" and "mask_backbone.geometry.2" in self._packed_tc
         if use_tc:
-            Yc, Zc = int(sizes[:, 1].max()), int(sizes[:, 2].max())
-            xoff = np.concatenate([[0], np.cumsum(sizes[:, 0] + 1)])
-            Xc = int(xoff[-1])
-            cs = np.array([Yc * Zc * 64, Zc * 64, 64], dtype=np.int64)
-            cstr = np.tile(cs, (nk, 1))
-            first, t_first = S.regions_array(scene_off, xoff[:-1] * cs[0], sizes, sizes, scene_str, cstr)
-            last, t_last = S.regions_array(xoff[:-1] * cs[0], offs[:-1] * ncls, sizes, sizes, cstr)
-            # brick list: every 8x4x4 brick of every crop
-            nb = (sizes + np.array([7, 3, 3])) // np.array([8, 4, 4])
-            cnt = nb.prod(1)
-            owner = np.repeat(np.arange(nk), cnt)
-            local = np.arange(int(cnt.sum())) - np.repeat(np.concatenate([[0], np.cumsum(cnt)[:-1]]), cnt)
-            bz = local % nb[owner, 2]
-            by = (local // nb[owner, 2]) % nb[owner, 1]
-            bx = local // (nb[owner, 2] * nb[owner, 1])
-            tiles = np.zeros((len(owner), 8), dtype=np.int32)
-            tiles[:, 0], tiles[:, 1], tiles[:, 2] = xoff[owner] + bx * 8, by * 4, bz * 4
-            tiles[:, 3], tiles[:, 4], tiles[:, 5] = xoff[owner] + sizes[owner, 0], sizes[owner, 1], sizes[owner, 2]
-            blob = np.concatenate([first.view(np.uint8), last.view(np.uint8), tiles.view(np.uint8).reshape(-1)])
-        else:
-            dstr = np.stack([sizes[:, 1] * sizes[:, 2] * 64, sizes[:, 2] * 64, np.full(nk, 64)], 1)
-            first, t_first = S.regions_array(scene_off, offs[:-1] * 64, sizes, sizes, scene_str)
-            mid, t_mid = S.regions_array(offs[:-1] * 64, offs[:-1] * 64, sizes, sizes, dstr)
-            last, t_last = S.regions_array(offs[:-1] * 64, offs[:-1] * ncls, sizes, sizes, dstr)
-            blob = np.concatenate([first.view(np.uint8), last.view(np.uint8), mid.view(np.uint8)])
-        stage = self._ws("mask_tables_host", blob.size, torch.uint8, dev, pinned=True)
-        stage.numpy()[:] = blob
-        tables = self._ws("mask_tables", blob.size, torch.uint8, dev)
-        tables.copy_(stage, non_blocking=True)
-        rb = nk * S.REGION_BYTES
-        r_first, r_last, r_rest = tables[:rb], tables[rb:2 * rb], tables[2 * rb:]
-        if use_tc:
+            Xc, Yc, Zc = (int(v) for v in plan.canvas)
+            n_tiles = int(plan.n_tiles_tc)
+            r_tiles = tables[plan.off_rest:plan.off_rest + 32 * n_tiles]
             cvox = Xc * Yc * Zc
             canv = self._ws("mask_canvas", 2 * cvox * 64, torch.float32, dev)
             canv.zero_()
@@ -513,20 +502,28 @@ class Network(nn.Module):
                 dst = Act(bufs[(li + 1) % 2], (Xc, Yc, Zc), 64)
                 tok = self._rec(f"conv_tc[{name}]")
                 S.check(S.lib.sis3d_conv3d_k3_tc(S.ptr(x.t), S.ptr(self._packed_tc[name]), None, None, 0, 0, S.ptr(dst.t), 64,
-                                                 0, Xc, Yc, Zc, 64, 64, 3, S.ptr(r_rest), tiles.shape[0], 1, S.stream()),
+                                                 0, Xc, Yc, Zc, 64, 64, 3, S.ptr(r_tiles), n_tiles, 1, S.stream()),
                         f"conv3d_k3_tc[{name}]")
                 self._rec_end(tok)
                 x = dst
         else:
+            r_mid, t_mid = tables[plan.off_rest:plan.off_rest + rb], int(plan.tiles_mid)
             act_buf = self._ws("mask_act", 2 * total * 64, torch.float32, dev)
             bufs = [act_buf[:total * 64], act_buf[total * 64:]]
             x = self._conv(scene, "mask_backbone.geometry.0", act=1, regions=(r_first, t_first), out_dims=(total, 1, 1),
                            out=Act(bufs[0], (total, 1, 1), 64))
             for li, idx in enumerate((2, 4, 6, 8)):
-                x = self._conv(x, f"mask_backbone.geometry.{idx}", act=1, regions=(r_rest, t_mid), out_dims=(total, 1, 1),
+                x = self._conv(x, f"mask_backbone.geometry.{idx}", act=1, regions=(r_mid, t_mid), out_dims=(total, 1, 1),
                                out=Act(bufs[(li + 1) % 2], (total, 1, 1), 64))
         y = self._conv(x, "mask_backbone.geometry.10", pad=0, act=2, regions=(r_last, t_last), out_dims=(total, 1, 1),
                        out=Act(outb, (total, 1, 1), ncls))
+        # predicted-class channel of every kept RoI, thresholded, packed: ONE small D2H for the driver
+        bits = torch.empty(total, dtype=torch.uint8, device=dev)
+        S.check(S.lib.sis3d_mask_select(S.ptr(y.t), S.ptr(d_offs), S.ptr(d_cls), nk, ncls, C.c_int64(total),
+                                        S.f32(cfg.MASK_THRESH), None, S.ptr(bits), S.stream()), "mask_select")
+        self._predictions["mask_bits"] = bits
+        self._predictions["mask_offsets"] = offs
+        self._predictions["mask_sizes"] = sizes
         masks = []
         for j in range(nk):
             w_, h_, l_ = (int(v) for v in sizes[j])
@@ -535,6 +532,20 @@ class Network(nn.Module):
         return masks
 
     # ------------------------------------------------------------------ forward
+    @staticmethod
+    def _carve(pack, R, nc):
+        """Typed views of the packed result buffer of the static stage (one buffer -> one clone / one copy)."""
+        o, out = 0, {}
+        for name, shape, dt in (("rois", (R, 6), torch.float32), ("scores", (R,), torch.float32), ("level_ids", (R,), torch.int32),
+                                ("num", (4,), torch.int32), ("cls_score", (R, nc), torch.float32),
+                                ("bbox_pred", (R, nc * 6), torch.float32), ("cls_prob", (R, nc), torch.float32),
+                                ("det", (R, 16), torch.float32), ("cls_pred", (R,), torch.int64)):
+            nb = int(np.prod(shape)) * torch.empty(0, dtype=dt).element_size()
+            o = (o + 15) // 16 * 16
+            out[name] = pack[o:o + nb].view(dt).view(*shape)
+            o += nb
+        return out, o
+
     def _static_stage(self, scene_t, dims, blobs=None, killing_inds=None, fused=None):
         """Every fixed-shape step: back-projection -> backbone -> RPN/NMS -> RoI pool -> classifier ->
         detection decode.  No host synchronisation inside, so the whole stage can be replayed as one CUDA
@@ -549,20 +560,23 @@ class Network(nn.Module):
         level1, level2 = self._backbone(scene, imageft)
         if self._keep_debug:
             P["level1_vc"], P["level2_vc"] = level1.t, level2.t
-        rois, scores, level_ids, num = self._region_proposal((level1, level2, None), dims)
-        out = dict(rois=rois, scores=scores, level_ids=level_ids, num=num)
+        R, nc = int(cfg.TEST.RPN_POST_NMS_TOP_N), max(int(cfg.NUM_CLASSES), 1)
+        probe, total = self._carve(torch.empty(1 << 22, dtype=torch.uint8, device="meta"), R, nc)
+        pack = torch.empty(total + 16, dtype=torch.uint8, device=dev)
+        out, _ = self._carve(pack, R, nc)
+        out["pack"] = pack
+        rois, scores, level_ids = out["rois"], out["scores"], out["level_ids"]
+        num = out["num"][:1]
+        out["num"] = num
+        self._region_proposal((level1, level2, None), dims, out=(rois, scores, level_ids, num))
         if cfg.USE_CLASS:
-            cls_score, bbox_pred = self._classify((level1, level2, None), rois, level_ids)
-            R, nc = rois.shape[0], int(cfg.NUM_CLASSES)
-            cls_prob = torch.empty(R, nc, dtype=torch.float32, device=dev)
-            cls_pred = torch.empty(R, dtype=torch.int64, device=dev)
-            det = torch.empty(R, 16, dtype=torch.float32, device=dev)
+            cls_score, bbox_pred = self._classify((level1, level2, None), rois, level_ids, out=(out["cls_score"], out["bbox_pred"]))
+            cls_prob, cls_pred, det = out["cls_prob"], out["cls_pred"], out["det"]
             tok = self._rec("detect_decode")
             S.check(S.lib.sis3d_detect_decode(S.ptr(rois), S.ptr(num), R, S.ptr(cls_score), S.ptr(bbox_pred), nc,
                                               *dims, S.f32(cfg.CLASS_THRESH), S.ptr(cls_prob), S.ptr(cls_pred),
                                               S.ptr(det), S.stream()), "detect_decode")
             self._rec_end(tok)
-            out.update(cls_score=cls_score, bbox_pred=bbox_pred, cls_prob=cls_prob, cls_pred=cls_pred, det=det)
         return out
 
     def _graph_state(self, key, dims, n_views, feat_c, dev):
@@ -631,7 +645,10 @@ class Network(nn.Module):
                         st["outs"] = self._static_stage(st["scene"], dims, blobs, None, fdev)
                     st["graph"] = g
                 st["graph"].replay()
-                outs = {k: v.clone() for k, v in st["outs"].items()}  # results must not alias the replay buffers
+                # results must not alias the replay buffers: ONE clone of the packed result buffer, then re-carve
+                pack = st["outs"]["pack"].clone()
+                outs, _ = self._carve(pack, int(cfg.TEST.RPN_POST_NMS_TOP_N), max(int(cfg.NUM_CLASSES), 1))
+                outs["num"] = outs["num"][:1]
                 scene_t = st["scene"]
             else:
                 scene_t = data.to(dev, torch.float32, non_blocking=True).contiguous()
@@ -641,8 +658,15 @@ class Network(nn.Module):
                                  depths=fused["depths"].to(dev, torch.float32, non_blocking=True).contiguous())
                 outs = self._static_stage(scene_t, dims, blobs, killing_inds, fused)
             self._scene = scene_t
-            # the one host round trip of the forward: RoI count + decoded detections (<= 13 KB)
-            n = int(outs["num"].item())
+            # the one host round trip of the forward: decoded detections with the RoI count in row 0 / col 15 (12.8 KB)
+            if cfg.USE_CLASS:
+                det_pin = self._ws("det_host", outs["det"].numel(), torch.float32, dev, pinned=True).view_as(outs["det"])
+                det_pin.copy_(outs["det"], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                det_all = det_pin.numpy()
+                n = int(det_all[0, 15])
+            else:
+                n = int(outs["num"].item())
             P["rois"], P["roi_scores"] = [outs["rois"][:n]], [outs["scores"][:n].view(-1, 1)]
             P["level_inds"] = [outs["level_ids"][:n].float()]
             if cfg.USE_CLASS:
@@ -650,7 +674,7 @@ class Network(nn.Module):
                 P["bbox_pred"] = outs["bbox_pred"][:n]
                 P["detections"] = outs["det"][:n]
                 if cfg.USE_MASK:
-                    det_host = outs["det"][:n].cpu().numpy() if n else np.zeros((0, 16), np.float32)
+                    det_host = det_all[:n].copy()
                     P["mask_pred"] = [self._mask_branch(scene_t, det_host, n)]
                     P["detections_host"] = det_host
         return P

@@ -206,9 +206,9 @@ def main():
         if readback:
             det = P["detections_host"]
             nbytes += det.nbytes
-            for m, row in zip(P["mask_pred"][0], det[det[:, 8] > 0.5]):
-                hm = m[0, int(row[7])].cpu()
-                nbytes += hm.numel() * 4
+            if (det[:, 8] > 0.5).any():  # thresholded predicted-class masks of all kept RoIs: one D2H
+                hm = P["mask_bits"].cpu()
+                nbytes += hm.numel()
         return P, nbytes
 
     def timed(inputs, readback, steps):

@@ -209,6 +209,24 @@ int sis3d_detect_decode(const float *rois, const int32_t *num_rois, int max_rois
                         int scene_x, int scene_y, int scene_z, float class_thresh,
                         float *cls_prob, int64_t *cls_pred, float *det, void *stream);
 
+/* Host-side planner of the ragged mask stage (CPU code, no CUDA calls): from the decoded detection table
+ * h_det [n][16] (sis3d_detect_decode layout) builds every table the six mask-head launches need into one host blob
+ * (ship it with a single pinned H2D copy).  use_canvas = 1: crops packed along x on a zero canvas of size plan.canvas
+ * (tensor-core path, brick list at off_rest); 0: compact per-crop buffers (region table of the middle layers at
+ * off_rest).  Returns SIS3D_EWORKSPACE with plan->bytes set when `capacity` is too small. */
+typedef struct sis3d_mask_plan {
+    int32_t n_kept, canvas[3], n_tiles_tc, tiles_first, tiles_last, tiles_mid;
+    int64_t total_voxels;
+    int64_t off_first, off_last, off_rest, off_offs, off_cls, off_kept, off_sizes, bytes;
+} sis3d_mask_plan;
+int sis3d_mask_plan_build(const float *h_det, int n, int X, int Y, int Z, int ncls, int use_canvas, void *h_blob,
+                          size_t capacity, sis3d_mask_plan *plan);
+
+/* Predicted-class mask channel of every kept RoI, packed back to back, optionally thresholded to bits
+ * (lib/model/trainval.py:900-908).  masks [total][ncls]; offs int64[n_crops+1] voxel offsets; cls int32[n_crops]. */
+int sis3d_mask_select(const float *masks, const int64_t *offs, const int32_t *cls, int n_crops, int ncls,
+                      int64_t total_hint, float thresh, float *out, uint8_t *bits, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
