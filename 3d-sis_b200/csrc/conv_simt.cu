@@ -92,9 +92,9 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_f32(const ConvArgs 
     const int ks2 = a.ks * a.ks;
     const int k_begin = a.k_per_split ? blockIdx.z * a.k_per_split : 0;
     const int k_end = a.k_per_split ? min(a.K, k_begin + a.k_per_split) : a.K;
-    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
-        // ---------------- gather A
-        float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+    // global -> register fetch of one K chunk (A gathered from the voxel tensor, B from the packed weights)
+    auto fetch = [&](int k0, float4 &av, float4 &bv) {
+        av = make_float4(0.f, 0.f, 0.f, 0.f);
         if (a.fast) {
             const int tap = k0 / a.cin, c0 = k0 - tap * a.cin + lq * 4;
             const int kx = tap / ks2, kr = tap - kx * ks2, ky = kr / a.ks, kz = kr - ky * a.ks;
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_f32(const ConvArgs 
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int k = k0 + lq * 4 + i;
-                if (lvalid && k < a.K) {
+                if (lvalid && k < k_end) {
                     const int tap = k / a.cin, c = k - tap * a.cin;
                     const int kx = tap / ks2, kr = tap - kx * ks2, ky = kr / a.ks, kz = kr - ky * a.ks;
                     const int ix = bx + kx, iy = by + ky, iz = bz + kz;
@@ -121,12 +121,15 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_f32(const ConvArgs 
             }
             av = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
         }
-        // ---------------- load B
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (b_thread) {
             const int k = k0 + bk, n = n0 + bc;
-            if (k < a.K && n < a.ldw) bv = __ldg(reinterpret_cast<const float4 *>(a.w + (int64_t)k * a.ldw + n));
+            if (k < k_end && n < a.ldw) bv = __ldg(reinterpret_cast<const float4 *>(a.w + (int64_t)k * a.ldw + n));
         }
+    };
+    float4 av, bv;
+    if (k_begin < k_end) fetch(k_begin, av, bv);
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
         __syncthreads();  // previous chunk fully consumed
         As[lq * 4 + 0][lr] = av.x;
         As[lq * 4 + 1][lr] = av.y;
@@ -134,6 +137,7 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_f32(const ConvArgs 
         As[lq * 4 + 3][lr] = av.w;
         if (b_thread) *reinterpret_cast<float4 *>(&Bs[bk][bc]) = bv;
         __syncthreads();
+        if (k0 + BK < k_end) fetch(k0 + BK, av, bv);  // next chunk's global loads fly while this one is multiplied
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
             float ar[TM];
@@ -212,53 +216,34 @@ __global__ void pack_conv_weight_kernel(const float *w, int cout, int cin, int k
 }
 
 // MaxPool3d(kernel 3, stride 1, pad 1) on VC; out-of-range taps ignored (PyTorch pads with -inf).
-// Sliding window along z: a thread owns (x, y, channel quad, z segment) and keeps the 3x3 (x,y) maxima of the last
-// three z slices in registers -> 9 loads per output instead of 27.
-constexpr int kPoolSeg = 12;
+// One thread per (voxel, channel quad); the 27 neighbours are L1/L2 hits (a z-sliding-window variant with 9 loads per
+// output was measured slower: too little parallelism at 24x12x24).
 __global__ void __launch_bounds__(256) maxpool3_vc_kernel(const float4 *in, float4 *out, int X, int Y, int Z, int C4, int out_ld4,
                                                           int out_coff4) {
-    const int nseg = (Z + kPoolSeg - 1) / kPoolSeg;
-    const int64_t total = (int64_t)X * Y * nseg * C4;
+    const int64_t total = (int64_t)X * Y * Z * C4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C4);
         int64_t v = i / C4;
-        const int seg = (int)(v % nseg);
-        v /= nseg;
+        const int z = (int)(v % Z);
+        v /= Z;
         const int y = (int)(v % Y), x = (int)(v / Y);
-        const int z0 = seg * kPoolSeg, z1 = min(Z, z0 + kPoolSeg);
-        const float ninf = -INFINITY;
-        float4 m_prev = make_float4(ninf, ninf, ninf, ninf), m_cur = m_prev;
-        auto slice = [&](int z) {
-            float4 m = make_float4(ninf, ninf, ninf, ninf);
-            if ((unsigned)z < (unsigned)Z) {
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = x + dx;
+            if ((unsigned)xx >= (unsigned)X) continue;
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int yy = y + dy;
+                if ((unsigned)yy >= (unsigned)Y) continue;
 #pragma unroll
-                for (int dx = -1; dx <= 1; ++dx) {
-                    const int xx = x + dx;
-                    if ((unsigned)xx >= (unsigned)X) continue;
-#pragma unroll
-                    for (int dy = -1; dy <= 1; ++dy) {
-                        const int yy = y + dy;
-                        if ((unsigned)yy >= (unsigned)Y) continue;
-                        const float4 q = __ldg(in + (((int64_t)xx * Y + yy) * Z + z) * C4 + c);
-                        m.x = fmaxf(m.x, q.x); m.y = fmaxf(m.y, q.y); m.z = fmaxf(m.z, q.z); m.w = fmaxf(m.w, q.w);
-                    }
+                for (int dz = -1; dz <= 1; ++dz) {
+                    const int zz = z + dz;
+                    if ((unsigned)zz >= (unsigned)Z) continue;
+                    const float4 q = __ldg(in + (((int64_t)xx * Y + yy) * Z + zz) * C4 + c);
+                    m.x = fmaxf(m.x, q.x); m.y = fmaxf(m.y, q.y); m.z = fmaxf(m.z, q.z); m.w = fmaxf(m.w, q.w);
                 }
             }
-            return m;
-        };
-        m_prev = slice(z0 - 1);
-        m_cur = slice(z0);
-        for (int z = z0; z < z1; ++z) {
-            const float4 m_next = slice(z + 1);
-            float4 o;
-            o.x = fmaxf(fmaxf(m_prev.x, m_cur.x), m_next.x);
-            o.y = fmaxf(fmaxf(m_prev.y, m_cur.y), m_next.y);
-            o.z = fmaxf(fmaxf(m_prev.z, m_cur.z), m_next.z);
-            o.w = fmaxf(fmaxf(m_prev.w, m_cur.w), m_next.w);
-            out[(((int64_t)x * Y + y) * Z + z) * out_ld4 + out_coff4 + c] = o;
-            m_prev = m_cur;
-            m_cur = m_next;
         }
+        out[(i / C4) * out_ld4 + out_coff4 + c] = m;
     }
 }
 
@@ -355,7 +340,7 @@ extern "C" int sis3d_linear(const float *x, const float *w_packed, const float *
 
 extern "C" int sis3d_maxpool3(const float *in, float *out, int out_ld, int out_coff, int X, int Y, int Z, int C, void *stream) {
     if (!in || !out || C % 4 != 0 || out_ld % 4 != 0 || out_coff % 4 != 0 || X <= 0 || Y <= 0 || Z <= 0) return SIS3D_EINVAL;
-    const int64_t total = (int64_t)X * Y * cdiv(Z, kPoolSeg) * (C / 4);
+    const int64_t total = (int64_t)X * Y * Z * (C / 4);
     const int blocks = (int)imin64(cdiv64(total, 256), 148 * 16);
     maxpool3_vc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4 *)in, (float4 *)out, X, Y, Z, C / 4, out_ld / 4, out_coff / 4);
     return finish_launch();

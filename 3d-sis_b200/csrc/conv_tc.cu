@@ -34,6 +34,7 @@ struct TcArgs {
     const int32_t *tiles;  // [n_tiles][8] = x0,y0,z0,x1,y1,z1,-,- (origin, exclusive valid end) or null
     int X, Y, Z, cin, cout, act, out_ld, out_coff, res_ld, res_coff;
     int tiles_y, tiles_z;
+    int gemm_m, gemm_chunks_per_split;  // KS == 0 (plain GEMM y = x W^T, split-K over blockIdx.z)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -137,8 +138,10 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
     const uint32_t tmem_base = *tmem_slot;
 
     // ---- which brick
-    int x0, y0, z0, x1, y1, z1;
-    if (a.tiles) {
+    int x0 = 0, y0 = 0, z0 = 0, x1 = 0, y1 = 0, z1 = 0;
+    if constexpr (KS == 0) {
+        // GEMM mode: rows instead of bricks (x0 = first row, set below)
+    } else if (a.tiles) {
         const int32_t *t = a.tiles + (size_t)blockIdx.x * 8;
         x0 = t[0]; y0 = t[1]; z0 = t[2]; x1 = t[3]; y1 = t[4]; z1 = t[5];
     } else {
@@ -148,9 +151,14 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
     }
     const int n0 = blockIdx.y * BN;
     const int kchunks = a.cin / TC_KC;
-    constexpr int TAPS = KS * KS * KS;  // 27 (3x3x3, pad 1) or 1 (1x1x1)
+    constexpr int TAPS = KS == 0 ? 1 : KS * KS * KS;  // 27 (3x3x3, pad 1) or 1 (1x1x1 / GEMM)
     constexpr int SHIFT = KS == 3 ? 1 : 0;
-    const int total = TAPS * kchunks;
+    int total = TAPS * kchunks, chunk0 = 0;
+    if constexpr (KS == 0) {  // split-K GEMM: this CTA owns K chunks [chunk0, chunk0 + total)
+        chunk0 = blockIdx.z * a.gemm_chunks_per_split;
+        total = max(0, min(a.gemm_chunks_per_split, kchunks - chunk0));
+        x0 = blockIdx.x * TC_BM;  // row offset m0
+    }
 
     if (threadIdx.x == 0) {
         // ===== TMA producer =====
@@ -162,8 +170,13 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
             const int tap = it / kchunks, kc = it - tap * kchunks;
             const int dx = tap / (KS * KS), dy = (tap / KS) % KS, dz = tap % KS;
             uint8_t *sa = smem + s * STAGE_BYTES;
-            tma_load_4d(sa, &tmA, full + s, kc * TC_KC, z0 + dz - SHIFT, y0 + dy - SHIFT, x0 + dx - SHIFT);
-            tma_load_2d(sa + TC_A_BYTES, &tmB, full + s, tap * a.cin + kc * TC_KC, n0);
+            if constexpr (KS == 0) {
+                tma_load_2d(sa, &tmA, full + s, (chunk0 + it) * TC_KC, x0);
+                tma_load_2d(sa + TC_A_BYTES, &tmB, full + s, (chunk0 + it) * TC_KC, n0);
+            } else {
+                tma_load_4d(sa, &tmA, full + s, kc * TC_KC, z0 + dz - SHIFT, y0 + dy - SHIFT, x0 + dx - SHIFT);
+                tma_load_2d(sa + TC_A_BYTES, &tmB, full + s, tap * a.cin + kc * TC_KC, n0);
+            }
         }
     } else if (threadIdx.x == 32) {
         // ===== MMA issuer =====
@@ -184,6 +197,28 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
         umma_commit(acc_ready);
     }
     __syncwarp();
+    if constexpr (KS == 0) {
+        // ===== GEMM epilogue: raw fp32 partial sums of this K split -> partial[z][m][n] (bias/ReLU in the reduce pass)
+        if (total > 0) mbar_wait(acc_ready, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int m = x0 + (int)threadIdx.x;
+        float *prow = a.out + ((int64_t)blockIdx.z * a.gemm_m + m) * a.out_ld + n0;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+            if (m < a.gemm_m) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4 *>(prow + c * 32 + j) =
+                        total > 0 ? make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+        return;
+    }
 
     // ===== epilogue: TMEM lane r == output row r of the brick =====
     mbar_wait(acc_ready, 0);
@@ -218,6 +253,17 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+}
+
+__global__ void gemm_splitk_reduce_kernel(const float *part, int splits, int64_t split_stride, const float *bias, float *y, int M,
+                                          int N, int act) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * N) return;
+    float v = 0.f;
+    for (int s = 0; s < splits; ++s) v += part[(int64_t)s * split_stride + i];  // fixed order -> deterministic
+    if (bias) v += bias[i % N];
+    if (act == 1) v = fmaxf(v, 0.f);
+    y[i] = v;
 }
 
 // weights [cout][cin][3][3][3] -> [cout][27*cin] with k = tap*cin + c
@@ -324,4 +370,66 @@ extern "C" int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const floa
         case 64: return launch_tc<64, 1>(tmA, tmB, a, n_tiles, s);
         default: return launch_tc<128, 1>(tmA, tmB, a, n_tiles, s);
     }
+}
+
+// ---- y[M][N] = act(x[M][K] . w[N][K]^T + b): fully connected layer on the tensor cores (TF32), split-K ------------
+static int gemm_tc_splits(int M, int N, int K) {
+    const int tiles = cdiv(M, TC_BM) * (N / (N >= 128 ? 128 : N));
+    const int chunks = K / TC_KC;
+    int splits = max(1, min(chunks / 4, (kNumSMs + tiles - 1) / tiles));
+    return splits;
+}
+extern "C" int sis3d_linear_tc_supported(int K, int N) { return (K % TC_KC == 0 && (N == 32 || N == 64 || N % 128 == 0)) ? 1 : 0; }
+extern "C" size_t sis3d_linear_tc_workspace_bytes(int M, int N, int K) {
+    return sizeof(float) * (size_t)gemm_tc_splits(M, N, K) * M * N + 16;
+}
+extern "C" int sis3d_linear_tc(const float *x, const float *w_nk, const float *bias, float *y, int M, int K, int N, int act,
+                               void *workspace, size_t workspace_bytes, void *stream) {
+    if (!x || !w_nk || !y || !workspace || M <= 0) return SIS3D_EINVAL;
+    if (!sis3d_linear_tc_supported(K, N)) return SIS3D_EUNSUPPORTED;
+    if (((uintptr_t)x | (uintptr_t)w_nk | (uintptr_t)workspace) & 15) return SIS3D_EINVAL;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return SIS3D_EUNSUPPORTED;
+    const int BN = N >= 128 ? 128 : N;
+    int splits = gemm_tc_splits(M, N, K);
+    const int chunks = K / TC_KC;
+    const int per = cdiv(chunks, splits);
+    splits = cdiv(chunks, per);
+    if (workspace_bytes < sizeof(float) * (size_t)splits * M * N) return SIS3D_EWORKSPACE;
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+        cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+        cuuint32_t box[2] = {TC_KC, TC_BM};
+        cuuint32_t estr[2] = {1, 1};
+        if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return SIS3D_EINVAL;
+        cuuint64_t dimsb[2] = {(cuuint64_t)K, (cuuint64_t)N};
+        cuuint32_t boxb[2] = {TC_KC, (cuuint32_t)BN};
+        if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)w_nk, dimsb, strides, boxb, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return SIS3D_EINVAL;
+    }
+    TcArgs a = {};
+    a.out = (float *)workspace; a.out_ld = N; a.cin = K; a.cout = N; a.gemm_m = M; a.gemm_chunks_per_split = per;
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 grid(cdiv(M, TC_BM), N / BN, splits);
+    int rc;
+    if (BN == 32) {
+        const size_t smem = (size_t)TcStages<32>::value * (TC_A_BYTES + 32 * 128) + 1280;
+        cudaFuncSetAttribute(conv3d_k3_tc_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        conv3d_k3_tc_kernel<32, 0><<<grid, 128, smem, s>>>(tmA, tmB, a);
+    } else if (BN == 64) {
+        const size_t smem = (size_t)TcStages<64>::value * (TC_A_BYTES + 64 * 128) + 1280;
+        cudaFuncSetAttribute(conv3d_k3_tc_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        conv3d_k3_tc_kernel<64, 0><<<grid, 128, smem, s>>>(tmA, tmB, a);
+    } else {
+        const size_t smem = (size_t)TcStages<128>::value * (TC_A_BYTES + 128 * 128) + 1280;
+        cudaFuncSetAttribute(conv3d_k3_tc_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        conv3d_k3_tc_kernel<128, 0><<<grid, 128, smem, s>>>(tmA, tmB, a);
+    }
+    gemm_splitk_reduce_kernel<<<cdiv(M * N, 256), 256, 0, s>>>((const float *)workspace, splits, (int64_t)M * N, bias, y, M, N, act);
+    rc = finish_launch(2);
+    return rc;
 }

@@ -101,67 +101,80 @@ __global__ void __launch_bounds__(128) roi_pool_vc_kernel(const float *feat1, co
 }
 
 // Tail of the RoI classifier (lib/nets/backbones.py:225-231 layers 2,4 + lib/nets/network.py:55-57 heads) in one
-// launch: 8 RoI rows per CTA, activations stay in shared memory, weights ([K][ldw] packed) stream from L2.
+// launch: 4 RoI rows per CTA, activations stay in shared memory.  Each layer streams its packed weights ([K][ldw]) through
+// shared memory in 32-row slabs loaded cooperatively (8 independent float4 loads per thread in flight, next slab
+// prefetched into registers while the current one is multiplied) -- a thread-per-output loop over global memory is
+// latency-bound (measured 55 us).
 constexpr int kMlpRows = 4;
+constexpr int kMlpSlab = 32;
+__device__ __forceinline__ void mlp_layer(const float (*xin)[256], int K, const float *w, int N, float *slab /*[32][256]*/,
+                                          float *acc /*[kMlpRows]*/) {
+    const int t = threadIdx.x;
+    const int ld = (N + 3) & ~3, ld4 = ld >> 2;
+    const int per_slab = kMlpSlab * ld4;            // float4 per slab
+    float4 pre[8];
+#pragma unroll
+    for (int r = 0; r < kMlpRows; ++r) acc[r] = 0.f;
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = t + j * 256;
+            pre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < per_slab && k0 + i / ld4 < K) pre[j] = __ldg(reinterpret_cast<const float4 *>(w + (int64_t)k0 * ld) + i);
+        }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < K; k0 += kMlpSlab) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = t + j * 256;
+            if (i < per_slab) reinterpret_cast<float4 *>(slab)[i] = pre[j];
+        }
+        __syncthreads();
+        if (k0 + kMlpSlab < K) fetch(k0 + kMlpSlab);
+        if (t < N) {
+            const int kn = min(kMlpSlab, K - k0);
+            for (int k = 0; k < kn; ++k) {
+                const float wv = slab[k * ld + t];
+#pragma unroll
+                for (int r = 0; r < kMlpRows; ++r) acc[r] = fmaf(xin[r][k0 + k], wv, acc[r]);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) mlp_tail_kernel(const float *x1, int R, int d1, const float *w2, const float *b2, int d2,
                                                        const float *w3, const float *b3, int d3, const float *wc,
                                                        const float *bc, int nc, const float *wb, const float *bb, int nb,
                                                        float *cls_score, float *bbox_pred) {
     __shared__ float sa[kMlpRows][256];
     __shared__ float sb[kMlpRows][256];
+    __shared__ __align__(16) float slab[kMlpSlab * 256];
     const int r0 = blockIdx.x * kMlpRows, t = threadIdx.x;
     for (int i = t; i < kMlpRows * d1; i += 256) {
         const int r = i / d1, k = i - r * d1;
         sa[r][k] = (r0 + r < R) ? x1[(int64_t)(r0 + r) * d1 + k] : 0.f;
     }
-    __syncthreads();
     float acc[kMlpRows];
-    if (t < d2) {  // layer 2: d1 -> d2, ReLU
-#pragma unroll
-        for (int r = 0; r < kMlpRows; ++r) acc[r] = 0.f;
-        const int ld = (d2 + 3) & ~3;
-#pragma unroll 8
-        for (int k = 0; k < d1; ++k) {
-            const float w = __ldg(w2 + (int64_t)k * ld + t);
-#pragma unroll
-            for (int r = 0; r < kMlpRows; ++r) acc[r] = fmaf(sa[r][k], w, acc[r]);
-        }
+    mlp_layer(sa, d1, w2, d2, slab, acc);  // starts with a __syncthreads(): sa is complete
+    if (t < d2)
 #pragma unroll
         for (int r = 0; r < kMlpRows; ++r) sb[r][t] = fmaxf(acc[r] + b2[t], 0.f);
-    }
-    __syncthreads();
-    if (t < d3) {  // layer 3: d2 -> d3, ReLU
-#pragma unroll
-        for (int r = 0; r < kMlpRows; ++r) acc[r] = 0.f;
-        const int ld = (d3 + 3) & ~3;
-#pragma unroll 8
-        for (int k = 0; k < d2; ++k) {
-            const float w = __ldg(w3 + (int64_t)k * ld + t);
-#pragma unroll
-            for (int r = 0; r < kMlpRows; ++r) acc[r] = fmaf(sb[r][k], w, acc[r]);
-        }
+    mlp_layer(sb, d2, w3, d3, slab, acc);
+    if (t < d3)
 #pragma unroll
         for (int r = 0; r < kMlpRows; ++r) sa[r][t] = fmaxf(acc[r] + b3[t], 0.f);
-    }
-    __syncthreads();
-    for (int o = t; o < nc + nb; o += 256) {  // heads: d3 -> nc (class scores) | nb (box deltas)
-        const bool is_cls = o < nc;
-        const int n = is_cls ? o : o - nc;
-        const float *w = is_cls ? wc : wb;
-        const int ld = ((is_cls ? nc : nb) + 3) & ~3;
-#pragma unroll
-        for (int r = 0; r < kMlpRows; ++r) acc[r] = 0.f;
-#pragma unroll 8
-        for (int k = 0; k < d3; ++k) {
-            const float wv = __ldg(w + (int64_t)k * ld + n);
-#pragma unroll
-            for (int r = 0; r < kMlpRows; ++r) acc[r] = fmaf(sa[r][k], wv, acc[r]);
-        }
-        const float bias = is_cls ? bc[n] : bb[n];
+    mlp_layer(sa, d3, wc, nc, slab, acc);
+    if (t < nc)
 #pragma unroll
         for (int r = 0; r < kMlpRows; ++r)
-            if (r0 + r < R) (is_cls ? cls_score : bbox_pred)[(int64_t)(r0 + r) * (is_cls ? nc : nb) + n] = acc[r] + bias;
-    }
+            if (r0 + r < R) cls_score[(int64_t)(r0 + r) * nc + t] = acc[r] + bc[t];
+    mlp_layer(sa, d3, wb, nb, slab, acc);
+    if (t < nb)
+#pragma unroll
+        for (int r = 0; r < kMlpRows; ++r)
+            if (r0 + r < R) bbox_pred[(int64_t)(r0 + r) * nb + t] = acc[r] + bb[t];
 }
 
 // Predicted-class channel of every kept RoI's mask, packed back to back (what the driver saves:
@@ -278,7 +291,8 @@ extern "C" int sis3d_mlp_tail(const float *x1, int R, int d1, const float *w2, c
                               const float *b3, int d3, const float *wc, const float *bc, int nc, const float *wb,
                               const float *bb, int nb, float *cls_score, float *bbox_pred, void *stream) {
     if (!x1 || !w2 || !b2 || !w3 || !b3 || !wc || !bc || !wb || !bb || !cls_score || !bbox_pred || R <= 0) return SIS3D_EINVAL;
-    if (d1 > 256 || d2 > 256 || d3 > 256 || d1 <= 0 || d2 <= 0 || d3 <= 0 || nc <= 0 || nb <= 0) return SIS3D_EUNSUPPORTED;
+    if (d1 > 256 || d2 > 256 || d3 > 256 || d1 <= 0 || d2 <= 0 || d3 <= 0 || nc <= 0 || nb <= 0 || nc > 256 || nb > 256)
+        return SIS3D_EUNSUPPORTED;
     mlp_tail_kernel<<<cdiv(R, kMlpRows), 256, 0, (cudaStream_t)stream>>>(x1, R, d1, w2, b2, d2, w3, b3, d3, wc, bc, nc, wb, bb, nb,
                                                                         cls_score, bbox_pred);
     return finish_launch();

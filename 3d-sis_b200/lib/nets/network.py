@@ -255,6 +255,15 @@ class Network(nn.Module):
         packed, bias, cout, cin, _ = self._packed[name]
         M = x.shape[0]
         y = torch.empty(M, cout, dtype=torch.float32, device=x.device)
+        if self._math == "tf32" and cin >= 1024 and S.lib.sis3d_linear_tc_supported(cin, cout):
+            w_nk = dict(self.named_parameters())[name + ".weight"].detach()  # nn.Linear layout [N][K] is already K-major
+            nbytes = int(S.lib.sis3d_linear_tc_workspace_bytes(M, cout, cin))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            tok = self._rec(f"linear_tc[{name}]")
+            S.check(S.lib.sis3d_linear_tc(S.ptr(x), S.ptr(w_nk), S.ptr(bias), S.ptr(y), M, cin, cout, act, S.ptr(ws),
+                                          C.c_size_t(nbytes), S.stream()), f"linear_tc[{name}]")
+            self._rec_end(tok)
+            return y
         nbytes = int(S.lib.sis3d_linear_workspace_bytes(M, cout, cin))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
         tok = self._rec(f"linear[{name}]")

@@ -140,6 +140,13 @@ size_t sis3d_linear_workspace_bytes(int M, int N, int K);
 int sis3d_linear(const float *x, const float *w_packed, const float *bias, float *y, int M, int K, int N,
                  int act, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Same layer on the tensor cores (tcgen05 TF32, fp32 accumulate, split-K + deterministic reduce): w_nk is the
+ * nn.Linear weight as stored, [N][K].  K % 32 == 0, N in {32, 64, 128k}. */
+int sis3d_linear_tc_supported(int K, int N);
+size_t sis3d_linear_tc_workspace_bytes(int M, int N, int K);
+int sis3d_linear_tc(const float *x, const float *w_nk, const float *bias, float *y, int M, int K, int N, int act,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
 /* Layers 2-3 of the classifier MLP and both heads in one launch (activations stay in shared memory):
  * x1 [R][d1] -> relu(W2) [d2] -> relu(W3) [d3] -> cls_score [R][nc] and bbox_pred [R][nb].  All weights packed by
  * sis3d_pack_conv_weight(ks=1); d1,d2,d3 <= 256.  (lib/nets/backbones.py:225-231, lib/nets/network.py:55-57) */

@@ -439,3 +439,27 @@ def test_linear_split_k(S, M, K, N, act):
                                    M, K, N, act, S.ptr(ws), C.c_size_t(nbytes), S.stream()))
         torch.cuda.synchronize()
         torch.testing.assert_close(y.cpu(), ref, atol=3e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("M,K,N,act", [(200, 8192, 256, 1), (61, 1024, 128, 0), (128, 256, 64, 1), (300, 2048, 32, 1)])
+def test_linear_tc_tf32(S, M, K, N, act):
+    """Fully connected layer on tcgen05 (2-D TMA operands, split-K, deterministic reduce) vs fp32."""
+    rng = np.random.default_rng(M + K + N)
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    w = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    ref = torch.from_numpy(x) @ torch.from_numpy(w).T + torch.from_numpy(b)
+    if act:
+        ref = F.relu(ref)
+    y = torch.full((M, N), 7.0, device=DEV)
+    nbytes = int(S.lib.sis3d_linear_tc_workspace_bytes(M, N, K))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    xd, wd, bd = torch.from_numpy(x).to(DEV), torch.from_numpy(w).to(DEV), torch.from_numpy(b).to(DEV)
+    outs = []
+    for _ in range(2):
+        S.check(S.lib.sis3d_linear_tc(S.ptr(xd), S.ptr(wd), S.ptr(bd), S.ptr(y), M, K, N, act, S.ptr(ws), C.c_size_t(nbytes), S.stream()))
+        torch.cuda.synchronize()
+        outs.append(y.cpu().clone())
+    assert torch.equal(outs[0], outs[1])
+    rel = ((outs[0] - ref).norm() / ref.norm()).item()
+    assert rel < 2e-3, rel
