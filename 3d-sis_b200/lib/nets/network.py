@@ -69,6 +69,7 @@ class Network(nn.Module):
         # conv math for the 3x3x3 layers: 'tf32' = tcgen05 tensor cores (default), 'fp32' = CUDA-core exact path
         self._math = os.environ.get("SIS3D_CONV_MATH", str(cfg.get("CONV_MATH", "tf32"))).lower()
         self._graphs = {}
+        self._slots = []
         self._sparse_color = os.environ.get("SIS3D_SPARSE_COLOR", "1") != "0"
         self._pack_dirty = True
         self._arena = {}  # grow-only device/pinned workspaces for the ragged (per-scene sized) stage
@@ -457,7 +458,7 @@ class Network(nn.Module):
             self._predictions["pool5"] = pool5
         return cls_score.t.view(R, -1), bbox_pred.t.view(R, -1)
 
-    def _mask_branch(self, scene_ncdhw, det_host, n):
+    def _mask_branch(self, scene_ncdhw, det_host, n, extras=None):
         """Ragged per-RoI mask head (reference: network.py:283-317).  All kept crops are packed along x on
         one zeroed canvas [sum(w_j + 1), max h, max l, 64] (one zero slab between crops = the crop-border
         zero padding), so each of the six layers is ONE launch: layer 1 (C_in = 2, windowed NCDHW scene) and
@@ -530,9 +531,8 @@ class Network(nn.Module):
         bits = torch.empty(total, dtype=torch.uint8, device=dev)
         S.check(S.lib.sis3d_mask_select(S.ptr(y.t), S.ptr(d_offs), S.ptr(d_cls), nk, ncls, C.c_int64(total),
                                         S.f32(cfg.MASK_THRESH), None, S.ptr(bits), S.stream()), "mask_select")
-        self._predictions["mask_bits"] = bits
-        self._predictions["mask_offsets"] = offs
-        self._predictions["mask_sizes"] = sizes
+        if extras is not None:
+            extras.update(mask_bits=bits, mask_offsets=offs, mask_sizes=sizes)
         masks = []
         for j in range(nk):
             w_, h_, l_ = (int(v) for v in sizes[j])
@@ -603,23 +603,40 @@ class Network(nn.Module):
         self._graphs[key] = st
         return st
 
-    def forward(self, blobs, mode="TEST", killing_inds=None):
-        if mode != "TEST":
-            raise NotImplementedError("only the inference (TEST) forward is implemented on the B200 path")
-        if not (cfg.USE_BACKBONE and cfg.USE_RPN):
-            raise NotImplementedError("USE_BACKBONE/USE_RPN=False (ground-truth RoIs) are training/ablation modes")
+    # -- a forward is three host steps; `forward` runs them back to back, `forward_pipelined` overlaps them across
+    #    consecutive scenes on three stream slots (each slot owns its graphs, static buffers and arena)
+    def _slot(self, i):
+        while len(self._slots) <= i:
+            self._slots.append(dict(stream=torch.cuda.Stream() if self._slots else None, graphs={}, arena={}))
+        return self._slots[i]
+
+    class _UseSlot:
+        def __init__(self, net, slot):
+            self.net, self.slot = net, slot
+
+        def __enter__(self):
+            n, sl = self.net, self.slot
+            self.saved = (n._graphs, n._arena)
+            n._graphs, n._arena = sl["graphs"], sl["arena"]
+            self.ctx = torch.cuda.stream(sl["stream"]) if sl["stream"] is not None else None
+            if self.ctx is not None:
+                self.ctx.__enter__()
+
+        def __exit__(self, *exc):
+            if self.ctx is not None:
+                self.ctx.__exit__(*exc)
+            self.net._graphs, self.net._arena = self.saved
+
+    def _submit(self, blobs, killing_inds, slot):
+        """Step 1 (async): input copies, static stage (graph replay), packed results -> pinned host (async D2H)."""
         self._ensure_packed()
         dev = next(self.parameters()).device
         data = blobs["data"]
         if data.shape[0] != 1:
             raise S.Sis3dError("batch size 1 only (as the reference's RoI pooling / proposal layer)")
-        self._scene_info = data.shape[2:]
-        self._id = blobs["id"][0] if "id" in blobs else None
-        self.batch_size = 1
-        self._mode = "TEST"
         dims = tuple(int(v) for v in data.shape[2:])
-        P = self._predictions
-        with torch.no_grad():
+        h = dict(slot=slot, dims=dims, id=blobs["id"][0] if "id" in blobs else None, scene_info=data.shape[2:])
+        with torch.no_grad(), Network._UseSlot(self, slot):
             lists = cfg.USE_IMAGES and "proj_ind_3d" in blobs
             use_graph = self._use_graph and not (self._keep_debug or self._prof is not None or lists)
             if cfg.USE_IMAGES and not cfg.USE_IMAGES_GT:
@@ -627,8 +644,8 @@ class Network(nn.Module):
             fused = None
             if cfg.USE_IMAGES and not lists:
                 imgs = blobs["nearest_images"]
-                w, h = int(cfg.DEPTH_SHAPE[0]), int(cfg.DEPTH_SHAPE[1])
-                vp = proj.view_params(cfg.INTRINSIC, (w, h), cfg.PROJ_DEPTH_MIN, cfg.PROJ_DEPTH_MAX, dims, None,
+                w, hh = int(cfg.DEPTH_SHAPE[0]), int(cfg.DEPTH_SHAPE[1])
+                vp = proj.view_params(cfg.INTRINSIC, (w, hh), cfg.PROJ_DEPTH_MIN, cfg.PROJ_DEPTH_MAX, dims, None,
                                       imgs["poses"][0], imgs["world2grid"][0])
                 fused = dict(vp=vp, feats=imgs["images"][0], depths=torch.as_tensor(imgs["depths"][0]))
             if use_graph:
@@ -666,13 +683,24 @@ class Network(nn.Module):
                                  feats=fused["feats"].to(dev, torch.float32, non_blocking=True),
                                  depths=fused["depths"].to(dev, torch.float32, non_blocking=True).contiguous())
                 outs = self._static_stage(scene_t, dims, blobs, killing_inds, fused)
-            self._scene = scene_t
-            # the one host round trip of the forward: decoded detections with the RoI count in row 0 / col 15 (12.8 KB)
+            h["outs"], h["scene_t"] = outs, scene_t
+            # the one host round trip of a scene: decoded detections with the RoI count in row 0 / col 15 (12.8 KB)
             if cfg.USE_CLASS:
                 det_pin = self._ws("det_host", outs["det"].numel(), torch.float32, dev, pinned=True).view_as(outs["det"])
                 det_pin.copy_(outs["det"], non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-                det_all = det_pin.numpy()
+                h["det_pin"] = det_pin
+            h["ev_static"] = torch.cuda.Event()
+            h["ev_static"].record()
+        return h
+
+    def _launch_ragged(self, h):
+        """Step 2: wait for the detections of this scene, plan + launch its ragged mask stage, queue the readback."""
+        h["ev_static"].synchronize()
+        outs = h["outs"]
+        P = {}
+        with torch.no_grad(), Network._UseSlot(self, h["slot"]):
+            if cfg.USE_CLASS:
+                det_all = h["det_pin"].numpy()
                 n = int(det_all[0, 15])
             else:
                 n = int(outs["num"].item())
@@ -684,9 +712,65 @@ class Network(nn.Module):
                 P["detections"] = outs["det"][:n]
                 if cfg.USE_MASK:
                     det_host = det_all[:n].copy()
-                    P["mask_pred"] = [self._mask_branch(scene_t, det_host, n)]
+                    extras = {}
+                    P["mask_pred"] = [self._mask_branch(h["scene_t"], det_host, n, extras)]
                     P["detections_host"] = det_host
-        return P
+                    P.update(extras)
+                    if "mask_bits" in extras:  # thresholded predicted-class masks -> pinned host, asynchronously
+                        bits = extras["mask_bits"]
+                        pin = self._ws("bits_host", bits.numel(), torch.uint8, bits.device, pinned=True)
+                        pin.copy_(bits, non_blocking=True)
+                        h["bits_pin"] = pin
+            h["ev_done"] = torch.cuda.Event()
+            h["ev_done"].record()
+        h["P"] = P
+        return h
+
+    def _finalize(self, h):
+        """Step 3: wait for the scene's last kernel / copy and hand out its predictions."""
+        h["ev_done"].synchronize()
+        P = h["P"]
+        if "bits_pin" in h:
+            P["mask_bits_host"] = h["bits_pin"].numpy().copy()
+        self._scene_info, self._id, self._scene = h["scene_info"], h["id"], h["scene_t"]
+        self.batch_size, self._mode = 1, "TEST"
+        self._predictions.clear()
+        self._predictions.update(P)
+        return self._predictions
+
+    def _check_mode(self, mode):
+        if mode != "TEST":
+            raise NotImplementedError("only the inference (TEST) forward is implemented on the B200 path")
+        if not (cfg.USE_BACKBONE and cfg.USE_RPN):
+            raise NotImplementedError("USE_BACKBONE/USE_RPN=False (ground-truth RoIs) are training/ablation modes")
+
+    def forward(self, blobs, mode="TEST", killing_inds=None):
+        """Reference-compatible synchronous forward of one scene (lib/nets/network.py:72,187-317)."""
+        self._check_mode(mode)
+        return self._finalize(self._launch_ragged(self._submit(blobs, killing_inds, self._slot(0))))
+
+    def forward_pipelined(self, blobs_iter, mode="TEST"):
+        """Throughput form of the scene loop (lib/model/trainval.py:787-822): yields (blobs, predictions) in order
+        while overlapping scene i+1's input copies + static stage and scene i's ragged mask stage with scene
+        i-1's read-back, on three stream slots.  The yielded dict is only valid until the next iteration."""
+        self._check_mode(mode)
+        from collections import deque
+        q = deque()
+        i = 0
+        for blobs in blobs_iter:
+            q.append([blobs, self._submit(blobs, None, self._slot(1 + i % 3)), False])
+            i += 1
+            if len(q) >= 2 and not q[-2][2]:
+                self._launch_ragged(q[-2][1])
+                q[-2][2] = True
+            if len(q) == 3:
+                b, h, _ = q.popleft()
+                yield b, self._finalize(h)
+        while q:
+            b, h, launched = q.popleft()
+            if not launched:
+                self._launch_ragged(h)
+            yield b, self._finalize(h)
 
     def delete_intermediate_states(self):
         self._predictions.clear()

@@ -26,7 +26,7 @@ def wall(fn, n=20):
     for _ in range(n): fn()
     torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e3
 
-st = list(net._graphs.values())[0]
+st = list(net._slots[0]["graphs"].values())[0]
 print("graph replay + sync        : %.3f ms" % wall(lambda: (st["graph"].replay(), torch.cuda.synchronize())))
 det = net._predictions["detections_host"]; n = det.shape[0]
 print("mask branch + sync (n=%d)  : %.3f ms" % (n, wall(lambda: (net._mask_branch(st["scene"], det, n), torch.cuda.synchronize()))))
