@@ -636,6 +636,7 @@ class Network(nn.Module):
             raise S.Sis3dError("batch size 1 only (as the reference's RoI pooling / proposal layer)")
         dims = tuple(int(v) for v in data.shape[2:])
         h = dict(slot=slot, dims=dims, id=blobs["id"][0] if "id" in blobs else None, scene_info=data.shape[2:])
+        before = set(self._predictions) if self._keep_debug else None
         with torch.no_grad(), Network._UseSlot(self, slot):
             lists = cfg.USE_IMAGES and "proj_ind_3d" in blobs
             use_graph = self._use_graph and not (self._keep_debug or self._prof is not None or lists)
@@ -691,6 +692,9 @@ class Network(nn.Module):
                 h["det_pin"] = det_pin
             h["ev_static"] = torch.cuda.Event()
             h["ev_static"].record()
+        if self._keep_debug:  # intermediate tensors the static stage left in _predictions (parity tests)
+            h["debug"] = {k: v for k, v in self._predictions.items()
+                          if k.startswith(("level", "rpn_", "pool5")) or k not in before}
         return h
 
     def _launch_ragged(self, h):
@@ -735,6 +739,7 @@ class Network(nn.Module):
         self._scene_info, self._id, self._scene = h["scene_info"], h["id"], h["scene_t"]
         self.batch_size, self._mode = 1, "TEST"
         self._predictions.clear()
+        self._predictions.update(h.get("debug", {}))
         self._predictions.update(P)
         return self._predictions
 

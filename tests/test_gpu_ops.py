@@ -110,8 +110,9 @@ def test_roi_pool_exact_both_layouts(oracle, S, C_, pool):
     lv[2::5] = 0
     top = torch.empty(n, C_ * pool ** 3, device=DEV)
     arg = torch.empty(n, C_ * pool ** 3, dtype=torch.int32, device=DEV)
-    S.check(S.lib.sis3d_roi_pool_levels(S.ptr(fvc), S.ptr((-fvc).contiguous()), None, S.ptr(lv), S.f32(0.25), n, 24, 12, 24,
-                                        C_, pool, pool, pool, S.ptr(torch.from_numpy(rois).to(DEV)), S.ptr(top), S.ptr(arg),
+    rois_d, neg_fvc = torch.from_numpy(rois).to(DEV), (-fvc).contiguous()  # keep device buffers alive across the async launch
+    S.check(S.lib.sis3d_roi_pool_levels(S.ptr(fvc), S.ptr(neg_fvc), None, S.ptr(lv), S.f32(0.25), n, 24, 12, 24,
+                                        C_, pool, pool, pool, S.ptr(rois_d), S.ptr(top), S.ptr(arg),
                                         S.stream()))
     want2, warg2 = oracle.roi_pool3d(-feat, rois, (pool,) * 3, 0.25)
     lvh = lv.cpu().numpy()
@@ -181,7 +182,8 @@ def test_conv3d_vs_torch_fp32(S, cin, cout, ks, stride, dims, bias, res, act):
             inp, strides, sc = torch.from_numpy(x[0]).to(DEV).contiguous(), (Y * Z, Z, 1), X * Y * Z
         regions, tiles = S.make_regions([dict(in_off=0, out_off=0, in_dim=dims, out_dim=od, in_stride=strides)], DEV)
         rd = torch.from_numpy(r[0]).to(DEV).permute(1, 2, 3, 0).contiguous() if res else None
-        S.check(S.lib.sis3d_conv3d(S.ptr(inp), C.c_int64(sc), S.ptr(packed), S.ptr(torch.from_numpy(b).to(DEV)) if bias else None,
+        bd = torch.from_numpy(b).to(DEV) if bias else None
+        S.check(S.lib.sis3d_conv3d(S.ptr(inp), C.c_int64(sc), S.ptr(packed), S.ptr(bd),
                                    S.ptr(rd), cout if res else 0, 0, S.ptr(out), cout + 4, 4, S.ptr(regions), 1, tiles, cin,
                                    cout, ks, stride, pad, act, S.stream()))
         got = out[..., 4:].permute(3, 0, 1, 2).cpu()
@@ -198,7 +200,8 @@ def test_conv3d_regions_zero_pad_at_crop_border(S):
     crops = [(2, 1, 3, 9, 8, 10), (5, 0, 0, 20, 12, 7)]
     sd = torch.from_numpy(scene).to(DEV)
     packed = torch.empty(54, 64, device=DEV)
-    S.check(S.lib.sis3d_pack_conv_weight(S.ptr(torch.from_numpy(w).to(DEV)), 64, 2, 3, S.ptr(packed), S.stream()))
+    wdev = torch.from_numpy(w).to(DEV)
+    S.check(S.lib.sis3d_pack_conv_weight(S.ptr(wdev), 64, 2, 3, S.ptr(packed), S.stream()))
     sizes = [(c[3] - c[0], c[4] - c[1], c[5] - c[2]) for c in crops]
     offs = np.concatenate([[0], np.cumsum([a * b * c for a, b, c in sizes])])
     out = torch.empty(int(offs[-1]) * 64, device=DEV)
@@ -367,10 +370,12 @@ def test_conv3d_tc_tf32_vs_fp32(S, cin, cout, dims, bias, res, act, ks):
         ref = F.relu(ref)
     xd = torch.from_numpy(x[0]).to(DEV).permute(1, 2, 3, 0).contiguous()
     wtc = torch.empty(cout, ks ** 3 * cin, device=DEV)
-    S.check(S.lib.sis3d_pack_conv_weight_tc(S.ptr(torch.from_numpy(w).to(DEV)), cout, cin, ks, S.ptr(wtc), S.stream()))
+    wdev = torch.from_numpy(w).to(DEV)
+    bdev = torch.from_numpy(b).to(DEV) if bias else None
+    S.check(S.lib.sis3d_pack_conv_weight_tc(S.ptr(wdev), cout, cin, ks, S.ptr(wtc), S.stream()))
     out = torch.full(dims + (cout + 4,), 7.0, device=DEV)
     rd = torch.from_numpy(r[0]).to(DEV).permute(1, 2, 3, 0).contiguous() if res else None
-    S.check(S.lib.sis3d_conv3d_k3_tc(S.ptr(xd), S.ptr(wtc), S.ptr(torch.from_numpy(b).to(DEV)) if bias else None, S.ptr(rd),
+    S.check(S.lib.sis3d_conv3d_k3_tc(S.ptr(xd), S.ptr(wtc), S.ptr(bdev), S.ptr(rd),
                                      cout if res else 0, 0, S.ptr(out), cout + 4, 4, *dims, cin, cout, ks, None, 0, act, S.stream()))
     torch.cuda.synchronize()
     got = out[..., 4:].permute(3, 0, 1, 2).cpu()
@@ -402,7 +407,8 @@ def test_conv3d_tc_tile_list(S):
                     tiles.append([x0 + bx, by, bz, x0 + s[0], s[1], s[2], 0, 0])
     td = torch.tensor(tiles, dtype=torch.int32, device=DEV)
     wtc = torch.empty(cout, 27 * cin, device=DEV)
-    S.check(S.lib.sis3d_pack_conv_weight_tc(S.ptr(torch.from_numpy(w).to(DEV)), cout, cin, 3, S.ptr(wtc), S.stream()))
+    wdev = torch.from_numpy(w).to(DEV)
+    S.check(S.lib.sis3d_pack_conv_weight_tc(S.ptr(wdev), cout, cin, 3, S.ptr(wtc), S.stream()))
     out = torch.zeros(Xc, Yc, Zc, cout, device=DEV)
     S.check(S.lib.sis3d_conv3d_k3_tc(S.ptr(canvas.to(DEV)), S.ptr(wtc), None, None, 0, 0, S.ptr(out), cout, 0, Xc, Yc, Zc, cin,
                                      cout, 3, S.ptr(td), len(tiles), 1, S.stream()))
@@ -429,13 +435,15 @@ def test_linear_split_k(S, M, K, N, act):
         ref = F.relu(ref)
     ldw = (N + 3) // 4 * 4
     packed = torch.empty(K, ldw, device=DEV)
-    S.check(S.lib.sis3d_pack_conv_weight(S.ptr(torch.from_numpy(w).to(DEV).reshape(N, K, 1, 1, 1).contiguous()), N, K, 1,
+    wdev = torch.from_numpy(w).to(DEV).reshape(N, K, 1, 1, 1).contiguous()
+    xdev, bdev = torch.from_numpy(x).to(DEV), torch.from_numpy(b).to(DEV)
+    S.check(S.lib.sis3d_pack_conv_weight(S.ptr(wdev), N, K, 1,
                                          S.ptr(packed), S.stream()))
     y = torch.empty(M, N, device=DEV)
     nbytes = int(S.lib.sis3d_linear_workspace_bytes(M, N, K))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
     for _ in range(2):  # twice: deterministic reduction order
-        S.check(S.lib.sis3d_linear(S.ptr(torch.from_numpy(x).to(DEV)), S.ptr(packed), S.ptr(torch.from_numpy(b).to(DEV)), S.ptr(y),
+        S.check(S.lib.sis3d_linear(S.ptr(xdev), S.ptr(packed), S.ptr(bdev), S.ptr(y),
                                    M, K, N, act, S.ptr(ws), C.c_size_t(nbytes), S.stream()))
         torch.cuda.synchronize()
         torch.testing.assert_close(y.cpu(), ref, atol=3e-5, rtol=1e-4)
