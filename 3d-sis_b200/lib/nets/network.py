@@ -70,6 +70,7 @@ class Network(nn.Module):
         self._math = os.environ.get("SIS3D_CONV_MATH", str(cfg.get("CONV_MATH", "tf32"))).lower()
         self._graphs = {}
         self._slots = []
+        self._replayed_kernels = 0  # libsis3d kernels executed through CUDA-graph replays
         self._sparse_color = os.environ.get("SIS3D_SPARSE_COLOR", "1") != "0"
         self._pack_dirty = True
         self._arena = {}  # grow-only device/pinned workspaces for the ragged (per-scene sized) stage
@@ -668,10 +669,12 @@ class Network(nn.Module):
                     self._static_stage(st["scene"], dims, blobs, None, fdev)
                     torch.cuda.synchronize()
                     g = torch.cuda.CUDAGraph()
+                    n0 = S.launch_count()
                     with torch.cuda.graph(g):
                         st["outs"] = self._static_stage(st["scene"], dims, blobs, None, fdev)
-                    st["graph"] = g
+                    st["graph"], st["n_kernels"] = g, S.launch_count() - n0
                 st["graph"].replay()
+                self._replayed_kernels += st["n_kernels"]
                 # results must not alias the replay buffers: ONE clone of the packed result buffer, then re-carve
                 pack = st["outs"]["pack"].clone()
                 outs, _ = self._carve(pack, int(cfg.TEST.RPN_POST_NMS_TOP_N), max(int(cfg.NUM_CLASSES), 1))
@@ -776,6 +779,10 @@ class Network(nn.Module):
             if not launched:
                 self._launch_ragged(h)
             yield b, self._finalize(h)
+
+    def kernel_launches(self):
+        """libsis3d kernels executed so far by this process: direct launches + kernels inside replayed graphs."""
+        return S.launch_count() + self._replayed_kernels
 
     def delete_intermediate_states(self):
         self._predictions.clear()

@@ -183,105 +183,42 @@ def main():
     math = os.environ.get("SIS3D_CONV_MATH", "tf32")
     net, cfg = make_net(CASES["cfg2_96x48x96"], keep_debug=False, math=math)
 
-    # distinct chunk per rank and per step slot (4 rotating inputs per rank)
-    n_in = 4
+    # 24 distinct chunks per rank rotate (24 x 6.9 MB = 166 MB > the 126 MB L2): host (pinned) and device copies
+    n_in = 24
     host_in, dev_in = [], []
     for j in range(n_in):
-        data, views = case(1000 + rank * 16 + j)
+        data, views = case(1000 + rank * 64 + j)
         hb = {"data": torch.from_numpy(data).pin_memory(), "id": ["bench"],
               "nearest_images": {k2: [torch.from_numpy(views[k1]).pin_memory()] for k1, k2 in
                                  (("feats", "images"), ("depths", "depths"), ("poses", "poses"), ("world2grid", "world2grid"))}}
         host_in.append(hb)
-        db = {"data": hb["data"].to(dev), "id": ["bench"],
-              "nearest_images": {"images": [hb["nearest_images"]["images"][0].to(dev)],
-                                 "depths": [hb["nearest_images"]["depths"][0].to(dev)],
-                                 "poses": hb["nearest_images"]["poses"], "world2grid": hb["nearest_images"]["world2grid"]}}
-        dev_in.append(db)
+        dev_in.append({"data": hb["data"].to(dev), "id": ["bench"],
+                       "nearest_images": {"images": [hb["nearest_images"]["images"][0].to(dev)],
+                                          "depths": [hb["nearest_images"]["depths"][0].to(dev)],
+                                          "poses": hb["nearest_images"]["poses"], "world2grid": hb["nearest_images"]["world2grid"]}})
     h2d = sum(t.numel() * t.element_size() for t in [host_in[0]["data"]] + [v[0] for v in host_in[0]["nearest_images"].values()])
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def step(blobs, readback):
-        P = net.forward(blobs, "TEST", None)
-        nbytes = 0
-        if readback:
-            det = P["detections_host"]
-            nbytes += det.nbytes
-            if (det[:, 8] > 0.5).any():  # thresholded predicted-class masks of all kept RoIs: one D2H
-                hm = P["mask_bits"].cpu()
-                nbytes += hm.numel()
-        return P, nbytes
+    def step(blobs):  # one synchronous forward (latency view / per-kernel timing pass)
+        return net.forward(blobs, "TEST", None)
 
-    def timed(inputs, readback, steps):
-        evs, launches0, d2h, vox, nroi, nmask = [], S.launch_count(), 0, 0, 0, 0
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        for i in range(steps):
-            flush.fill_(i & 255)  # L2 flush between timed iterations (not timed)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            P, nb = step(inputs[i % n_in], readback)
-            e1.record()
-            evs.append((e0, e1))
-            d2h += nb
-            det = P["detections_host"]
-            k = det[det[:, 8] > 0.5]
-            vox += int(((k[:, 12] - k[:, 9]) * (k[:, 13] - k[:, 10]) * (k[:, 14] - k[:, 11])).sum())
-            nroi += det.shape[0]
-            nmask += k.shape[0]
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ms = sum(a.elapsed_time(b) for a, b in evs)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), S.launch_count() - launches0, d2h / steps, vox / steps, nroi / steps, nmask / steps
-
-    for i in range(args.warmup):
-        step(dev_in[i % n_in], False)
-        step(host_in[i % n_in], True)
-    if args.host_profile and rank == 0:
-        import cProfile
-        import io
-        import pstats
-        pr = cProfile.Profile()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        pr.enable()
-        for i in range(args.host_profile):
-            step(dev_in[i % n_in], False)
-        pr.disable()
-        wall = (time.perf_counter() - t0) / args.host_profile * 1e3
-        buf = io.StringIO()
-        pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(45)
-        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", "host_profile.txt"), "w") as f:
-            f.write(f"wall ms per forward (device-resident inputs): {wall:.3f}\n" + buf.getvalue())
-    clocks = Clocks(local)
-    if rank == 0:
-        clocks.start()
-    ms_dev, launches, _, vox, nroi, nmask = timed(dev_in, False, args.steps)
-    ms_e2e_sync, _, d2h_sync, _, _, _ = timed(host_in, True, args.steps)
-
-    # e2e through the scene-loop API (Network.forward_pipelined): host buffers in, detections + thresholded masks
-    # out on the host, three scenes in flight.  24 distinct pinned input sets (166 MB > L2) rotate.
-    many = list(host_in)
-    for j in range(n_in, 24):
-        data, views = case(1000 + rank * 64 + j)
-        many.append({"data": torch.from_numpy(data).pin_memory(), "id": ["bench"],
-                     "nearest_images": {k2: [torch.from_numpy(views[k1]).pin_memory()] for k1, k2 in
-                                        (("feats", "images"), ("depths", "depths"), ("poses", "poses"), ("world2grid", "world2grid"))}})
-
-    def timed_pipelined(steps):
-        d2h = 0
+    def timed_loop(inputs, steps):
+        """K scenes through the scene-loop API (Network.forward_pipelined, 3 scenes in flight); every scene's
+        detections and thresholded predicted-class masks are read back to the host.  CUDA events on the default
+        stream bracket the region (it waits for the slot streams), barrier + synchronize on both sides."""
+        d2h, vox, nroi, nmask = 0, 0, 0, 0
+        k0 = net.kernel_launches()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _, P in net.forward_pipelined(many[i % len(many)] for i in range(steps)):
-            d2h += P["detections_host"].nbytes + (P["mask_bits_host"].nbytes if "mask_bits_host" in P else 0)
+        for _, P in net.forward_pipelined(inputs[i % n_in] for i in range(steps)):
+            det = P["detections_host"]
+            d2h += det.nbytes + (P["mask_bits_host"].nbytes if "mask_bits_host" in P else 0)
+            k = det[det[:, 8] > 0.5]
+            vox += int(((k[:, 12] - k[:, 9]) * (k[:, 13] - k[:, 10]) * (k[:, 14] - k[:, 11])).sum())
+            nroi += det.shape[0]
+            nmask += k.shape[0]
         for sl in net._slots:
             if sl["stream"] is not None:
                 torch.cuda.current_stream().wait_stream(sl["stream"])
@@ -292,16 +229,54 @@ def main():
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), d2h / steps
+        return float(t.item()), net.kernel_launches() - k0, d2h / steps, vox / steps, nroi / steps, nmask / steps
 
-    timed_pipelined(max(6, args.warmup))  # warm-up: captures the graphs of the three pipeline slots
-    ms_e2e, d2h = timed_pipelined(args.steps)
+    def latency(inputs, steps):
+        ts = []
+        for i in range(steps):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step(inputs[i % n_in])
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts))
+
+    for i in range(args.warmup):
+        step(dev_in[i % n_in])
+    timed_loop(dev_in, max(6, args.warmup))   # captures the graphs of the three pipeline slots
+    timed_loop(host_in, max(6, args.warmup))
+    if args.host_profile and rank == 0:
+        import cProfile
+        import io
+        import pstats
+        pr = cProfile.Profile()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pr.enable()
+        for i in range(args.host_profile):
+            step(dev_in[i % n_in])
+        pr.disable()
+        wall = (time.perf_counter() - t0) / args.host_profile * 1e3
+        buf = io.StringIO()
+        pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(45)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "host_profile.txt"), "w") as f:
+            f.write(f"wall ms per forward (device-resident inputs): {wall:.3f}\n" + buf.getvalue())
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    ms_dev, launches, _, vox, nroi, nmask = timed_loop(dev_in, args.steps)
+    ms_e2e, _, d2h, _, _, _ = timed_loop(host_in, args.steps)
     clocks.stop_flag = True
+    lat_dev = latency(dev_in, min(args.steps, 20))
+    lat_host = latency(host_in, min(args.steps, 20))
 
     # per-kernel device time of the dominant kernel family, CUDA events on the launching stream
     net._prof = {}
     for i in range(min(args.steps, 5)):
-        step(dev_in[i % n_in], False)
+        step(dev_in[i % n_in])
     torch.cuda.synchronize()
     prof = {k: (sum(a.elapsed_time(b) for a, b in v) / min(args.steps, 5), len(v) // min(args.steps, 5)) for k, v in net._prof.items()}
     net._prof = None
@@ -324,6 +299,16 @@ def main():
         pass
     alg = ALG_BYTES + MASK_BYTES_PER_VOXEL * vox
     kernel_ms = sum(v[0] for v in prof.values())
+    # dominant tensor-core kernel: rpn_net_level{1,2} = 3x3x3 conv 128->256 on 24x12x24 = 12.231 GFLOP per launch
+    rpn_ms = [v[0] for k, v in prof.items() if k.startswith("conv_tc[rpn_net_level")]
+    tensor_roof = None
+    if rpn_ms:
+        tf = 12.231e9 / (float(np.mean(rpn_ms)) * 1e-3) / 1e12
+        tensor_roof = {"bound": "tensor", "kernel": "conv3d_k3_tc_kernel<128,3> (rpn_net_level1/2, TF32 in, fp32 accumulate)",
+                       "achieved": tf, "peak": tflops / 2.0, "unit": "TFLOP/s", "frac": tf / (tflops / 2.0),
+                       "peak_note": "TF32 dense = half of the measured bf16 GEMM peak in MEASURED_PEAKS.json (no TF32 figure measured)",
+                       "flops_per_launch": 12.231e9, "ms_per_launch": float(np.mean(rpn_ms)),
+                       "traffic": 525.0e6, "traffic_note": "l1tex__m_xbar2l1tex_read_bytes of the <64> instance in profiles/ (L2->SM operand feed; DRAM ~12 MB)"}
     out = {
         "metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -331,21 +316,26 @@ def main():
         "data": "synthetic",
         "config": {"workload": "96x48x96 ScanNet-shape chunk, 5 views, full rpn_class_mask_5 TEST forward (cfg2)",
                    "conv_math": math, "inputs": "seeded synthetic TSDF + ENet-shaped features/depth/poses; seeded synthetic weights",
-                   "l2": "256 MiB flush write between timed iterations (untimed)", "rois_per_step": nroi,
+                   "l2": "24 distinct chunks per rank rotate: 166 MB of inputs > 126 MB L2 (no flush kernel)",
+                   "api": "Network.forward_pipelined (the scene loop; 3 scenes in flight on 3 streams)", "rois_per_step": nroi,
                    "mask_rois_per_step": nmask, "mask_voxels_per_step": vox, "chunks_per_rank": args.steps,
                    "parallelism": f"chunk-sharded dp{world}"},
         "e2e": {"value": e2e_v, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps,
-                "api": "Network.forward_pipelined (scene loop, 3 scenes in flight; pinned host buffers in, detections + "
-                       "thresholded predicted-class masks back on the host); 24 rotating input sets = 166 MB > L2",
-                "sync_forward": {"value": world * args.steps / (ms_e2e_sync / 1e3), "ms_per_step": ms_e2e_sync / args.steps,
-                                 "d2h_bytes_per_step": d2h_sync}},
+                "what": "same loop from pinned HOST buffers: H2D of scene+features+depth+poses and D2H of detections + "
+                        "thresholded predicted-class masks inside the timed region"},
+        "latency_ms": {"sync_forward_device_inputs": lat_dev, "sync_forward_host_inputs": lat_host,
+                       "note": "median of single synchronous Network.forward calls (no overlap between scenes)"},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "achieved": alg / (kernel_ms * 1e-3) / 1e9 if kernel_ms else None, "peak": hbm,
-                     "unit": "GB/s", "frac": (alg / (kernel_ms * 1e-3) / 1e9 / hbm) if kernel_ms else None, "traffic": None,
-                     "peak_source": which, "kernel": "whole forward (all libsis3d launches of one step)",
-                     "kernel_ms_per_step": kernel_ms, "algorithmic_bytes_per_step": alg,
-                     "conv_ms_per_step": conv_ms, "top_kernels_ms": {k: round(v[0], 4) for k, v in top}},
+        # fraction of the 3D-conv HBM roofline = ALG_BYTES x scenes/s per GPU / HBM peak.  ALG_BYTES are the
+        # per-layer compulsory fp32 bytes of the reference's dataflow; the fused/sparse design moves far fewer.
+        "roofline": {"bound": "hbm", "achieved": alg * (value / world) / 1e9, "peak": hbm, "unit": "GB/s",
+                     "frac": alg * (value / world) / 1e9 / hbm, "traffic": None, "peak_source": which,
+                     "kernel": "whole forward = all libsis3d launches of one scene (graph replay + ragged mask stage)",
+                     "algorithmic_bytes_per_step": alg, "gpu_ms_per_step": per_step_ms,
+                     "eager_kernel_ms_per_step": kernel_ms, "conv_ms_per_step": conv_ms,
+                     "top_kernels_ms": {k: round(v[0], 4) for k, v in top}},
+        "roofline_tensor_kernel": tensor_roof,
         "clocks": clocks.summary(),
     }
     if not args.no_cpu_baseline and world == 1:
