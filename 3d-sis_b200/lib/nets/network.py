@@ -70,6 +70,7 @@ class Network(nn.Module):
         self._math = os.environ.get("SIS3D_CONV_MATH", str(cfg.get("CONV_MATH", "tf32"))).lower()
         self._graphs = {}
         self._slots = []
+        self._branches = os.environ.get("SIS3D_BRANCHES", "1") != "0"
         self._replayed_kernels = 0  # libsis3d kernels executed through CUDA-graph replays
         self._sparse_color = os.environ.get("SIS3D_SPARSE_COLOR", "1") != "0"
         self._pack_dirty = True
@@ -378,6 +379,26 @@ class Network(nn.Module):
         self._rec_end(tok)
         return Act(vol, dims, feats.shape[1])
 
+    def _parallel(self, fns):
+        """Run independent launch sequences as parallel branches: forked side streams that join back, which CUDA-graph
+        capture records as concurrent graph branches.  The layers at 24x12x24 launch only 54-108 CTAs on 148 SMs, so
+        independent stacks (colour || geometry, RPN level 1 || level 2) overlap instead of queueing."""
+        if not self._branches or self._prof is not None or len(fns) < 2:
+            return [f() for f in fns]
+        cur = torch.cuda.current_stream()
+        key = ("branch_streams", cur.device)
+        side = self._const(key, lambda: [torch.cuda.Stream() for _ in range(3)])[:len(fns) - 1]
+        out = [None] * len(fns)
+        for st in side:
+            st.wait_stream(cur)
+        for i, st in enumerate(side, 1):
+            with torch.cuda.stream(st):
+                out[i] = fns[i]()
+        out[0] = fns[0]()
+        for st in side:
+            cur.wait_stream(st)
+        return out
+
     def _backbone(self, scene: Act, imageft: Act):
         """reference: backbones.py:98-113.  Concatenation is free: both producers write their slice of
         the level-1 tensor directly (colour channels first, then geometry)."""
@@ -386,14 +407,18 @@ class Network(nn.Module):
         if cfg.USE_IMAGES:
             d4 = tuple((d // 2) // 2 for d in scene.dims)
             level1 = Act(torch.empty(*d4, 128, dtype=torch.float32, device=dev), d4, 128)
-            if isinstance(imageft, tuple):  # ("color0", act): color.0 already produced by the fused sparse path
-                self._run_stack(imageft[1], "color", spec["color"][1:],
-                                final_out=lambda x, op: Act(level1.t, d4, 64, ld=128, coff=0))
-            else:
-                self._run_stack(imageft, "color", spec["color"],
-                                final_out=lambda x, op: Act(level1.t, d4, 64, ld=128, coff=0))
-            self._run_stack(scene, "geometry1", spec["geometry1"],
-                            final_out=lambda x, op: Act(level1.t, d4, 64, ld=128, coff=64))
+            def colour():
+                if isinstance(imageft, tuple):  # ("color0", act): color.0 already produced by the fused sparse path
+                    return self._run_stack(imageft[1], "color", spec["color"][1:],
+                                           final_out=lambda x, op: Act(level1.t, d4, 64, ld=128, coff=0))
+                return self._run_stack(imageft, "color", spec["color"],
+                                       final_out=lambda x, op: Act(level1.t, d4, 64, ld=128, coff=0))
+
+            def geometry():
+                return self._run_stack(scene, "geometry1", spec["geometry1"],
+                                       final_out=lambda x, op: Act(level1.t, d4, 64, ld=128, coff=64))
+
+            self._parallel([colour, geometry])
         else:
             level1 = self._run_stack(scene, "geometry1", spec["geometry1"])
         level2 = self._run_stack(level1, "geometry2", spec["geometry2"])
@@ -401,13 +426,19 @@ class Network(nn.Module):
 
     def _region_proposal(self, feats, dims, out=None):
         """reference: network.py:537-587 + 657-683 (softmax/anchors/decode/top-N/NMS fused on device)."""
-        levels = []
-        for lvl, f in enumerate(feats, 1):
-            A = cfg["NUM_ANCHORS_LEVEL%d" % lvl]
-            if not A or f is None:
-                continue
+        def head(lvl, f, A):
             h = self._conv(f, f"rpn_net_level{lvl}", act=1)
             heads = self._conv(h, f"rpn_heads_level{lvl}")  # [N, 2A + 6A]
+            heads.t.record_stream(torch.cuda.current_stream())
+            return heads
+
+        todo = [(lvl, f, cfg["NUM_ANCHORS_LEVEL%d" % lvl]) for lvl, f in enumerate(feats, 1)
+                if f is not None and cfg["NUM_ANCHORS_LEVEL%d" % lvl]]
+        main = torch.cuda.current_stream()
+        outs = self._parallel([(lambda t=t: head(*t)) for t in todo])
+        levels = []
+        for (lvl, f, A), heads in zip(todo, outs):
+            heads.t.record_stream(main)
             cls = Act(heads.t, f.dims, 2 * A, ld=8 * A, coff=0)
             bbox = Act(heads.t.reshape(-1)[2 * A:], f.dims, 6 * A, ld=8 * A, coff=0)
             name = cfg["ANCHORS_TYPE_LEVEL%d" % lvl]

@@ -93,34 +93,37 @@ def weights():
     return synth.make_weights(seed=0)
 
 
-class Clocks(threading.Thread):
-    """nvidia-smi clock / throttle sampling during the timed region."""
+class Clocks:
+    """nvidia-smi clock / throttle sampling during the timed region (one long-lived `-lms 100` process)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.proc, self.stop_flag = index, None, False
 
-    def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([t.strip() for t in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def summary(self):
-        if not self.rows:
+        rows = []
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+                out, _ = self.proc.communicate(timeout=5)
+                rows = [[t.strip() for t in ln.split(",")] for ln in out.splitlines() if ln.strip()]
+            except Exception:
+                pass
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(rows[0][1]) if rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(rows)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -159,7 +162,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="sis3d")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
@@ -267,11 +270,12 @@ def main():
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
+        time.sleep(0.3)
     ms_dev, launches, _, vox, nroi, nmask = timed_loop(dev_in, args.steps)
     ms_e2e, _, d2h, _, _, _ = timed_loop(host_in, args.steps)
     clocks.stop_flag = True
-    lat_dev = latency(dev_in, min(args.steps, 20))
-    lat_host = latency(host_in, min(args.steps, 20))
+    lat_dev = latency(dev_in, min(args.steps, 30))
+    lat_host = latency(host_in, min(args.steps, 30))
 
     # per-kernel device time of the dominant kernel family, CUDA events on the launching stream
     net._prof = {}
