@@ -9,6 +9,7 @@
 // k = tap*C_in + c.  A is gathered on the fly from the VC (or strided NCDHW) input with zero fill
 // outside the region (== PyTorch zero padding of the *crop*, lib/nets/network.py:303-311); B is the
 // pre-packed weight [K][ldw].
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace sis3d {
@@ -29,6 +30,7 @@ struct ConvArgs {
     int dense_m;          // > 0: no region table, input is a dense [dense_m][cin] matrix (linear layer)
     int k_per_split;      // > 0: split-K, blockIdx.z owns K range [z*k_per_split, ...), raw partials to out + z*split_stride
     int64_t split_stride;
+    __half *out16;        // optional fp16 twin of the output, same element offsets as `out` (`out` may then be null)
 };
 
 template <int BN, int TM>
@@ -168,7 +170,8 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_f32(const ConvArgs 
             const int ox = m / oyz, orem = m - ox * oyz, oy = orem / R.out_dim[2], oz = orem - oy * R.out_dim[2];
             ooff = ox * R.out_stride[0] + oy * R.out_stride[1] + oz * R.out_stride[2];
         }
-        float *orow = a.out + R.out_off + ooff + a.out_coff;
+        const int64_t eoff = R.out_off + ooff + a.out_coff;
+        float *orow = a.out ? a.out + eoff : nullptr;
         if (a.k_per_split) {  // raw partial sums; bias/activation applied by splitk_reduce_kernel
             orow = a.out + (int64_t)blockIdx.z * a.split_stride + (int64_t)m * a.out_ld;
 #pragma unroll
@@ -188,7 +191,8 @@ __global__ void __launch_bounds__(kConvThreads) conv3d_igemm_f32(const ConvArgs 
             if (rrow) v += rrow[n];
             if (a.act == 1) v = fmaxf(v, 0.f);
             else if (a.act == 2) v = 1.f / (1.f + expf(-v));
-            orow[n] = v;
+            if (orow) orow[n] = v;
+            if (a.out16) a.out16[eoff + n] = __float2half_rn(v);
         }
     }
 }
@@ -282,7 +286,15 @@ extern "C" int sis3d_conv3d(const float *in, int64_t in_chan_stride, const float
                             const float *residual, int res_ld, int res_coff, float *out, int out_ld, int out_coff,
                             const sis3d_region *regions, int n_regions, int n_tiles, int cin, int cout, int ks,
                             int stride, int pad, int act, void *stream) {
-    if (!in || !w_packed || !out || !regions || n_regions <= 0 || cin <= 0 || cout <= 0) return SIS3D_EINVAL;
+    return sis3d_conv3d_ex(in, in_chan_stride, w_packed, bias, residual, res_ld, res_coff, out, nullptr, out_ld, out_coff, regions,
+                           n_regions, n_tiles, cin, cout, ks, stride, pad, act, stream);
+}
+
+extern "C" int sis3d_conv3d_ex(const float *in, int64_t in_chan_stride, const float *w_packed, const float *bias,
+                               const float *residual, int res_ld, int res_coff, float *out, uint16_t *out16, int out_ld,
+                               int out_coff, const sis3d_region *regions, int n_regions, int n_tiles, int cin, int cout, int ks,
+                               int stride, int pad, int act, void *stream) {
+    if (!in || !w_packed || (!out && !out16) || !regions || n_regions <= 0 || cin <= 0 || cout <= 0) return SIS3D_EINVAL;
     if (n_tiles <= 0) return SIS3D_OK;
     ConvArgs a;
     a.in = in; a.w = w_packed; a.bias = bias; a.res = residual; a.out = out; a.regions = regions;
@@ -290,7 +302,7 @@ extern "C" int sis3d_conv3d(const float *in, int64_t in_chan_stride, const float
     a.pad = pad; a.act = act; a.K = ks * ks * ks * cin; a.out_ld = out_ld; a.out_coff = out_coff;
     a.res_ld = res_ld; a.res_coff = res_coff; a.in_sc = in_chan_stride;
     a.fast = (in_chan_stride == 1 && cin % 16 == 0 && ((uintptr_t)in % 16 == 0)) ? 1 : 0;
-    a.dense_m = 0; a.k_per_split = 0; a.split_stride = 0;
+    a.dense_m = 0; a.k_per_split = 0; a.split_stride = 0; a.out16 = (__half *)out16;
     cudaStream_t s = (cudaStream_t)stream;
     if (cout <= 32) {
         dim3 grid(n_tiles, cdiv(cout, 32));
@@ -319,7 +331,7 @@ extern "C" int sis3d_linear(const float *x, const float *w_packed, const float *
     a.in = x; a.w = w_packed; a.bias = bias; a.res = nullptr; a.out = y; a.regions = nullptr; a.n_regions = 0;
     a.cin = K; a.cout = N; a.ldw = (N + 3) & ~3; a.ks = 1; a.stride = 1; a.pad = 0; a.act = act; a.K = K;
     a.out_ld = N; a.out_coff = 0; a.res_ld = 0; a.res_coff = 0; a.in_sc = 1; a.fast = 1; a.dense_m = M;
-    a.k_per_split = 0; a.split_stride = 0;
+    a.k_per_split = 0; a.split_stride = 0; a.out16 = nullptr;
     if (splits > 1) {
         if (!workspace || workspace_bytes < sizeof(float) * (size_t)splits * M * N) return SIS3D_EWORKSPACE;
         a.k_per_split = cdiv(cdiv(K, splits), BK) * BK;

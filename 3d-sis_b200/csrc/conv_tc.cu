@@ -18,6 +18,7 @@
 // Reference call sites: Bottleneck.conv2 (lib/nets/backbones.py:21), geometry2.0 (:216),
 // rpn_net_level{1,2} (lib/nets/network.py:40,45), MaskBackbone.geometry.{2,4,6,8} (backbones.py:243-249).
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace sis3d {
@@ -35,6 +36,7 @@ struct TcArgs {
     int X, Y, Z, cin, cout, act, out_ld, out_coff, res_ld, res_coff;
     int tiles_y, tiles_z;
     int gemm_m, gemm_chunks_per_split;  // KS == 0 (plain GEMM y = x W^T, split-K over blockIdx.z)
+    __half *out16;                      // optional fp16 twin of the output (same geometry as `out`); `out` may be null
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -73,14 +75,25 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
 }
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 // start>>4 [0,14) | LBO=1 [16,30) | SBO=1024B>>4 [32,46) | version=1 [46,48) | layout=SWIZZLE_128B(2) [61,64)
+// ROWB = 128: SWIZZLE_128B (layout 2, 8-row atom = 1024 B);  ROWB = 64: SWIZZLE_64B (layout 4, 8-row atom = 512 B)
+template <int ROWB>
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    constexpr uint64_t sbo = (8 * ROWB) >> 4, layout = ROWB == 128 ? 2 : 4;
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
         : "memory");
 }
@@ -108,11 +121,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
 template <int BN>
 struct TcStages { static constexpr int value = BN >= 128 ? 4 : 3; };
 
-template <int BN, int KS>
+// EB = operand element bytes: 4 -> fp32 storage, kind::tf32;  2 -> fp16 storage, kind::f16 (same 11-bit significand,
+// half the operand bytes through L2).  ROWB = bytes of one K slice row in shared memory (128, or 64 for C_in = 32 in fp16).
+template <int BN, int KS, int EB = 4, int ROWB = 128>
 __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
-    constexpr int B_BYTES = BN * 128;
-    constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+    constexpr int KC = ROWB / EB;            // channels per pipeline stage
+    constexpr int A_BYTES = TC_BM * ROWB;
+    constexpr int B_BYTES = BN * ROWB;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int TC_STAGES = TcStages<BN>::value;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B needs 1024 B alignment
@@ -150,7 +167,7 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
         x1 = min(x0 + TC_BX, a.X); y1 = min(y0 + TC_BY, a.Y); z1 = min(z0 + TC_BZ, a.Z);
     }
     const int n0 = blockIdx.y * BN;
-    const int kchunks = a.cin / TC_KC;
+    const int kchunks = a.cin / KC;
     constexpr int TAPS = KS == 0 ? 1 : KS * KS * KS;  // 27 (3x3x3, pad 1) or 1 (1x1x1 / GEMM)
     constexpr int SHIFT = KS == 3 ? 1 : 0;
     int total = TAPS * kchunks, chunk0 = 0;
@@ -171,27 +188,30 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
             const int dx = tap / (KS * KS), dy = (tap / KS) % KS, dz = tap % KS;
             uint8_t *sa = smem + s * STAGE_BYTES;
             if constexpr (KS == 0) {
-                tma_load_2d(sa, &tmA, full + s, (chunk0 + it) * TC_KC, x0);
-                tma_load_2d(sa + TC_A_BYTES, &tmB, full + s, (chunk0 + it) * TC_KC, n0);
+                tma_load_2d(sa, &tmA, full + s, (chunk0 + it) * KC, x0);
+                tma_load_2d(sa + A_BYTES, &tmB, full + s, (chunk0 + it) * KC, n0);
             } else {
-                tma_load_4d(sa, &tmA, full + s, kc * TC_KC, z0 + dz - SHIFT, y0 + dy - SHIFT, x0 + dx - SHIFT);
-                tma_load_2d(sa + TC_A_BYTES, &tmB, full + s, tap * a.cin + kc * TC_KC, n0);
+                tma_load_4d(sa, &tmA, full + s, kc * KC, z0 + dz - SHIFT, y0 + dy - SHIFT, x0 + dx - SHIFT);
+                tma_load_2d(sa + A_BYTES, &tmB, full + s, tap * a.cin + kc * KC, n0);
             }
         }
     } else if (threadIdx.x == 32) {
         // ===== MMA issuer =====
         // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
         // A,B K-major, N>>3 at [17,23), M>>4 at [24,29)
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        constexpr uint32_t fmt = EB == 4 ? 2u : 0u;  // F16F32Format: 2 = TF32, 0 = F16
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
         for (int it = 0; it < total; ++it) {
             const int s = it % TC_STAGES;
             const uint32_t ph = (it / TC_STAGES) & 1;
             mbar_wait(full + s, ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + TC_A_BYTES;
+            const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
 #pragma unroll
-            for (int k = 0; k < TC_KC / 8; ++k)  // UMMA_K = 8 tf32 = 32 B: advance the start address inside the swizzle atom
-                umma_tf32(tmem_base, umma_desc(sa + k * 32), umma_desc(sb + k * 32), idesc, (it | k) ? 1u : 0u);
+            for (int k = 0; k < ROWB / 32; ++k) {  // one MMA consumes 32 B of K (8 tf32 / 16 f16): advance inside the swizzle atom
+                if constexpr (EB == 4) umma_tf32(tmem_base, umma_desc<ROWB>(sa + k * 32), umma_desc<ROWB>(sb + k * 32), idesc, (it | k) ? 1u : 0u);
+                else umma_f16(tmem_base, umma_desc<ROWB>(sa + k * 32), umma_desc<ROWB>(sb + k * 32), idesc, (it | k) ? 1u : 0u);
+            }
             umma_commit(empty + s);  // frees the smem slot once these MMAs retire
         }
         umma_commit(acc_ready);
@@ -227,7 +247,8 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
     const int vz = z0 + (r & 3), vy = y0 + ((r >> 2) & 3), vx = x0 + (r >> 4);
     const bool valid = vx < x1 && vy < y1 && vz < z1;
     const int64_t vox = ((int64_t)vx * a.Y + vy) * a.Z + vz;
-    float *orow = a.out + vox * a.out_ld + a.out_coff + n0;
+    float *orow = a.out ? a.out + vox * a.out_ld + a.out_coff + n0 : nullptr;
+    __half *hrow = a.out16 ? a.out16 + vox * a.out_ld + a.out_coff + n0 : nullptr;
     const float *rrow = a.res ? a.res + vox * a.res_ld + a.res_coff + n0 : nullptr;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
@@ -246,7 +267,14 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
                     o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
                 }
                 if (a.act == 1) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                *reinterpret_cast<float4 *>(orow + c * 32 + j) = o;
+                if (orow) *reinterpret_cast<float4 *>(orow + c * 32 + j) = o;
+                if (hrow) {
+                    const __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t *>(&h0);
+                    pk.y = *reinterpret_cast<const uint32_t *>(&h1);
+                    *reinterpret_cast<uint2 *>(hrow + c * 32 + j) = pk;
+                }
             }
         }
     }
@@ -291,18 +319,43 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-template <int BN, int KS>
+template <int BN, int KS, int EB = 4, int ROWB = 128>
 static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcArgs &a, int n_tiles, cudaStream_t s) {
-    const size_t smem = (size_t)TcStages<BN>::value * (TC_A_BYTES + BN * 128) + 1024 + 256;
+    const size_t smem = (size_t)TcStages<BN>::value * (TC_BM * ROWB + BN * ROWB) + 1024 + 256;
     static bool attr_done = false;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(conv3d_k3_tc_kernel<BN, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(conv3d_k3_tc_kernel<BN, KS, EB, ROWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return SIS3D_ELAUNCH;
         attr_done = true;
     }
     dim3 grid(n_tiles, a.cout / BN);
-    conv3d_k3_tc_kernel<BN, KS><<<grid, 128, smem, s>>>(tmA, tmB, a);
+    conv3d_k3_tc_kernel<BN, KS, EB, ROWB><<<grid, 128, smem, s>>>(tmA, tmB, a);
     return finish_launch();
+}
+
+// fp32 [cout][cin][taps] -> fp16 [cout][taps*cin] (k = tap*cin + c), round to nearest even
+__global__ void pack_conv_weight_tc_f16_kernel(const float *w, int cout, int cin, int taps, __half *out) {
+    const int64_t total = (int64_t)cout * taps * cin;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cin);
+        const int tap = (int)((i / cin) % taps);
+        const int n = (int)(i / ((int64_t)cin * taps));
+        out[i] = __float2half_rn(w[((int64_t)n * cin + c) * taps + tap]);
+    }
+}
+// VC fp32 (row stride in_ld, channel offset in_coff) -> dense VC fp16 [rows][C]
+__global__ void cast_f16_kernel(const float *in, int in_ld, int in_coff, int64_t rows, int C4, __half *out) {
+    const int64_t total = rows * C4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / C4;
+        const int c = (int)(i - r * C4) * 4;
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(in + r * in_ld + in_coff + c));
+        const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t *>(&h0);
+        pk.y = *reinterpret_cast<const uint32_t *>(&h1);
+        *reinterpret_cast<uint2 *>(out + r * (int64_t)C4 * 4 + c) = pk;
+    }
 }
 
 }  // namespace sis3d
@@ -351,7 +404,7 @@ extern "C" int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const floa
             return SIS3D_EINVAL;
     }
     TcArgs a;
-    a.bias = bias; a.res = residual; a.out = out; a.tiles = tiles;
+    a.bias = bias; a.res = residual; a.out = out; a.tiles = tiles; a.out16 = nullptr;
     a.X = X; a.Y = Y; a.Z = Z; a.cin = cin; a.cout = cout; a.act = act;
     a.out_ld = out_ld; a.out_coff = out_coff; a.res_ld = res_ld; a.res_coff = res_coff;
     a.tiles_y = cdiv(Y, TC_BY); a.tiles_z = cdiv(Z, TC_BZ);
@@ -432,4 +485,77 @@ extern "C" int sis3d_linear_tc(const float *x, const float *w_nk, const float *b
     gemm_splitk_reduce_kernel<<<cdiv(M * N, 256), 256, 0, s>>>((const float *)workspace, splits, (int64_t)M * N, bias, y, M, N, act);
     rc = finish_launch(2);
     return rc;
+}
+
+// ---- fp16-operand variant (kind::f16): activations and weights stored as fp16, fp32 accumulation in TMEM ----------
+extern "C" int sis3d_pack_conv_weight_tc_f16(const float *w, int cout, int cin, int ks, uint16_t *w16, void *stream) {
+    if (!w || !w16 || cout <= 0 || cin <= 0 || (ks != 1 && ks != 3)) return SIS3D_EINVAL;
+    const int taps = ks * ks * ks;
+    const int64_t total = (int64_t)cout * taps * cin;
+    pack_conv_weight_tc_f16_kernel<<<(int)imin64(cdiv64(total, 256), 148 * 8), 256, 0, (cudaStream_t)stream>>>(w, cout, cin, taps, (__half *)w16);
+    return finish_launch();
+}
+extern "C" int sis3d_cast_f16(const float *in, int in_ld, int in_coff, int64_t rows, int C, uint16_t *out, void *stream) {
+    if (!in || !out || rows <= 0 || C % 4 != 0 || (in_ld | in_coff) & 3) return SIS3D_EINVAL;
+    cast_f16_kernel<<<(int)imin64(cdiv64(rows * (C / 4), 256), 148 * 8), 256, 0, (cudaStream_t)stream>>>(in, in_ld, in_coff, rows, C / 4, (__half *)out);
+    return finish_launch();
+}
+extern "C" int sis3d_conv3d_tc_f16(const uint16_t *in16, const uint16_t *w16, const float *bias, const float *residual,
+                                   int res_ld, int res_coff, float *out32, uint16_t *out16, int out_ld, int out_coff, int X, int Y,
+                                   int Z, int cin, int cout, int ks, const int32_t *tiles, int n_tiles, int act, void *stream) {
+    if (!in16 || !w16 || (!out32 && !out16) || X <= 0 || Y <= 0 || Z <= 0 || (ks != 1 && ks != 3)) return SIS3D_EINVAL;
+    const int taps = ks * ks * ks;
+    if (!sis3d_conv3d_k3_tc_supported(cin, cout)) return SIS3D_EUNSUPPORTED;
+    if (((uintptr_t)in16 | (uintptr_t)w16 | (uintptr_t)out32 | (uintptr_t)out16) & 15) return SIS3D_EINVAL;
+    if ((out_ld | out_coff | res_ld | res_coff) & 3) return SIS3D_EINVAL;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return SIS3D_EUNSUPPORTED;
+    const int BN = cout >= 128 ? 128 : cout;
+    const bool wide = cin % 64 == 0;       // 64 channels = 128 B rows; C_in = 32 -> 64 B rows (SWIZZLE_64B)
+    const int kc = wide ? 64 : 32;
+    if (!wide && BN == 128) return SIS3D_EUNSUPPORTED;
+    const CUtensorMapSwizzle sw = wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X};
+        cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)Z * cin * 2, (cuuint64_t)Y * Z * cin * 2};
+        cuuint32_t box[4] = {(cuuint32_t)kc, TC_BZ, TC_BY, TC_BX};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void *)in16, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return SIS3D_EINVAL;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)taps * cin, (cuuint64_t)cout};
+        cuuint64_t strides[1] = {(cuuint64_t)taps * cin * 2};
+        cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)BN};
+        cuuint32_t estr[2] = {1, 1};
+        if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void *)w16, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return SIS3D_EINVAL;
+    }
+    TcArgs a = {};
+    a.bias = bias; a.res = residual; a.out = out32; a.out16 = (__half *)out16; a.tiles = tiles;
+    a.X = X; a.Y = Y; a.Z = Z; a.cin = cin; a.cout = cout; a.act = act;
+    a.out_ld = out_ld; a.out_coff = out_coff; a.res_ld = res_ld; a.res_coff = res_coff;
+    a.tiles_y = cdiv(Y, TC_BY); a.tiles_z = cdiv(Z, TC_BZ);
+    if (!tiles) n_tiles = cdiv(X, TC_BX) * a.tiles_y * a.tiles_z;
+    if (n_tiles <= 0) return SIS3D_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (wide) {
+        if (ks == 3) {
+            switch (BN) {
+                case 32: return launch_tc<32, 3, 2, 128>(tmA, tmB, a, n_tiles, s);
+                case 64: return launch_tc<64, 3, 2, 128>(tmA, tmB, a, n_tiles, s);
+                default: return launch_tc<128, 3, 2, 128>(tmA, tmB, a, n_tiles, s);
+            }
+        }
+        switch (BN) {
+            case 32: return launch_tc<32, 1, 2, 128>(tmA, tmB, a, n_tiles, s);
+            case 64: return launch_tc<64, 1, 2, 128>(tmA, tmB, a, n_tiles, s);
+            default: return launch_tc<128, 1, 2, 128>(tmA, tmB, a, n_tiles, s);
+        }
+    }
+    if (ks == 3) return BN == 32 ? launch_tc<32, 3, 2, 64>(tmA, tmB, a, n_tiles, s) : launch_tc<64, 3, 2, 64>(tmA, tmB, a, n_tiles, s);
+    return BN == 32 ? launch_tc<32, 1, 2, 64>(tmA, tmB, a, n_tiles, s) : launch_tc<64, 1, 2, 64>(tmA, tmB, a, n_tiles, s);
 }

@@ -12,6 +12,7 @@
 //   3. sparse_combine_kernel : per output voxel add its (<= 8) tap contributions in tap order, ReLU.
 // The result equals relu(conv3d(imageft, W, stride 2)) up to fp32 summation order; summation order is
 // fixed (no atomics on data), so results are run-to-run reproducible.
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace sis3d {
@@ -143,7 +144,8 @@ __global__ void __launch_bounds__(256) sparse_gemm_kernel(const SparseArgs a, co
     }
 }
 
-__global__ void __launch_bounds__(256) sparse_combine_kernel(const SparseArgs a, int cout, float *out, int out_ld, int out_coff) {
+__global__ void __launch_bounds__(256) sparse_combine_kernel(const SparseArgs a, int cout, float *out, int out_ld, int out_coff,
+                                                             __half *out16) {
     const int c4n = cout / 4;
     const int64_t total = (int64_t)a.n1 * c4n;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -160,6 +162,13 @@ __global__ void __launch_bounds__(256) sparse_combine_kernel(const SparseArgs a,
         }
         s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f);
         *reinterpret_cast<float4 *>(out + o * out_ld + out_coff + c4 * 4) = s;
+        if (out16) {
+            const __half2 h0 = __floats2half2_rn(s.x, s.y), h1 = __floats2half2_rn(s.z, s.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t *>(&h0);
+            pk.y = *reinterpret_cast<const uint32_t *>(&h1);
+            *reinterpret_cast<uint2 *>(out16 + o * out_ld + out_coff + c4 * 4) = pk;
+        }
     }
 }
 
@@ -201,6 +210,14 @@ extern "C" int sis3d_backproject_conv_k2s2(const float *feats, float *feats_t, c
                                            const int32_t *n_pairs, int n_views, int C, int img_w, int img_h, int X, int Y,
                                            int Z, const float *w_packed, int cout, float *out, int out_ld, int out_coff,
                                            void *workspace, size_t workspace_bytes, void *stream) {
+    return sis3d_backproject_conv_k2s2_ex(feats, feats_t, pix, pairs, n_pairs, n_views, C, img_w, img_h, X, Y, Z, w_packed, cout, out,
+                                          nullptr, out_ld, out_coff, workspace, workspace_bytes, stream);
+}
+
+extern "C" int sis3d_backproject_conv_k2s2_ex(const float *feats, float *feats_t, const int16_t *pix, const int32_t *pairs,
+                                              const int32_t *n_pairs, int n_views, int C, int img_w, int img_h, int X, int Y,
+                                              int Z, const float *w_packed, int cout, float *out, uint16_t *out16, int out_ld,
+                                              int out_coff, void *workspace, size_t workspace_bytes, void *stream) {
     if (!feats || !feats_t || !pix || !pairs || !n_pairs || !w_packed || !out || !workspace) return SIS3D_EINVAL;
     if (C % 16 != 0 || (cout != 32 && cout != 64) || (out_ld | out_coff) & 3 || n_views <= 0) return SIS3D_EUNSUPPORTED;
     SparseArgs a;
@@ -228,6 +245,6 @@ extern "C" int sis3d_backproject_conv_k2s2(const float *feats, float *feats_t, c
         sparse_gemm_kernel<32><<<kNumSMs * 2, 256, smem, s>>>(a, w_packed);
     }
     sparse_combine_kernel<<<(int)imin64(cdiv64((int64_t)a.n1 * (cout / 4), 256), kNumSMs * 8), 256, 0, s>>>(a, cout, out, out_ld,
-                                                                                                             out_coff);
+                                                                                                             out_coff, (__half *)out16);
     return finish_launch(4);
 }

@@ -176,15 +176,25 @@ class Network(nn.Module):
                 wtc = torch.empty(cout, ks ** 3 * cin, dtype=torch.float32, device=w.device)
                 S.check(S.lib.sis3d_pack_conv_weight_tc(S.ptr(w), cout, cin, ks, S.ptr(wtc), S.stream()), "pack_tc")
                 self._packed_tc[base] = wtc
-        for lvl in (1, 2, 3):  # both RPN heads of a level as ONE 1x1 conv: [2A | 6A] output channels
+        for lvl in (1, 2, 3):  # both RPN heads of a level as ONE 1x1 conv: [2A | 6A] output channels, zero-padded to a
+            # tensor-core friendly width (32/64/128k) so the merged head runs on the tcgen05 kernel as well
             c, b = f"rpn_cls_score_net_level{lvl}.0", f"rpn_bbox_pred_net_level{lvl}"
             if c + ".weight" in params and b + ".weight" in params:
-                w = torch.cat([params[c + ".weight"], params[b + ".weight"]], 0).detach().float().contiguous()
-                bias = torch.cat([params[c + ".bias"], params[b + ".bias"]], 0).detach().float().contiguous()
+                w = torch.cat([params[c + ".weight"], params[b + ".weight"]], 0).detach().float()
+                bias = torch.cat([params[c + ".bias"], params[b + ".bias"]], 0).detach().float()
                 cout, cin = w.shape[0], w.shape[1]
-                packed = torch.empty(cin, (cout + 3) // 4 * 4, dtype=torch.float32, device=w.device)
-                S.check(S.lib.sis3d_pack_conv_weight(S.ptr(w), cout, cin, 1, S.ptr(packed), S.stream()), "pack")
-                self._packed[f"rpn_heads_level{lvl}"] = (packed, bias, cout, cin, 1)
+                cpad = 32 if cout <= 32 else (64 if cout <= 64 else (cout + 127) // 128 * 128)
+                wp = torch.zeros(cpad, cin, 1, 1, 1, dtype=torch.float32, device=w.device)
+                wp[:cout] = w
+                bp = torch.zeros(cpad, dtype=torch.float32, device=w.device)
+                bp[:cout] = bias
+                packed = torch.empty(cin, cpad, dtype=torch.float32, device=w.device)
+                S.check(S.lib.sis3d_pack_conv_weight(S.ptr(wp), cpad, cin, 1, S.ptr(packed), S.stream()), "pack")
+                self._packed[f"rpn_heads_level{lvl}"] = (packed, bp, cpad, cin, 1)
+                if S.lib.sis3d_conv3d_k3_tc_supported(cin, cpad):
+                    wtc = torch.empty(cpad, cin, dtype=torch.float32, device=w.device)
+                    S.check(S.lib.sis3d_pack_conv_weight_tc(S.ptr(wp), cpad, cin, 1, S.ptr(wtc), S.stream()), "pack_tc")
+                    self._packed_tc[f"rpn_heads_level{lvl}"] = wtc
         torch.cuda.current_stream().synchronize()
         self._packed_version = v
 
@@ -428,7 +438,7 @@ class Network(nn.Module):
         """reference: network.py:537-587 + 657-683 (softmax/anchors/decode/top-N/NMS fused on device)."""
         def head(lvl, f, A):
             h = self._conv(f, f"rpn_net_level{lvl}", act=1)
-            heads = self._conv(h, f"rpn_heads_level{lvl}")  # [N, 2A + 6A]
+            heads = self._conv(h, f"rpn_heads_level{lvl}")  # [N, ld]: [2A class logits | 6A box deltas | zero pad]
             heads.t.record_stream(torch.cuda.current_stream())
             return heads
 
@@ -439,15 +449,15 @@ class Network(nn.Module):
         levels = []
         for (lvl, f, A), heads in zip(todo, outs):
             heads.t.record_stream(main)
-            cls = Act(heads.t, f.dims, 2 * A, ld=8 * A, coff=0)
-            bbox = Act(heads.t.reshape(-1)[2 * A:], f.dims, 6 * A, ld=8 * A, coff=0)
+            ld = heads.C  # padded head width
+            cls = Act(heads.t, f.dims, 2 * A, ld=ld, coff=0)
+            bbox = Act(heads.t.reshape(-1)[2 * A:], f.dims, 6 * A, ld=ld, coff=0)
             name = cfg["ANCHORS_TYPE_LEVEL%d" % lvl]
             sizes = self._const(("anchors", name, f.t.device), lambda: torch.tensor(
                 read_anchor_sizes(name), dtype=torch.float32, device=f.t.device).contiguous())
             if sizes.shape[0] != A:
                 raise S.Sis3dError(f"anchor table {name} has {sizes.shape[0]} rows, cfg says {A}")
-            levels.append(dict(cls=cls.t, deltas=bbox.t, sizes=sizes, grid=f.dims, A=A, cls_mode=0, cls_ld=8 * A,
-                               deltas_ld=8 * A))
+            levels.append(dict(cls=cls.t, deltas=bbox.t, sizes=sizes, grid=f.dims, A=A, cls_mode=0, cls_ld=ld, deltas_ld=ld))
             if self._keep_debug:
                 self._predictions[f"rpn_heads_level{lvl}"] = heads.t  # [..., :2A] class logits, [..., 2A:] box deltas
         tok = self._rec("rpn_proposals")

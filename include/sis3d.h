@@ -169,6 +169,28 @@ int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const float *bias, co
                        int res_ld, int res_coff, float *out, int out_ld, int out_coff, int X, int Y,
                        int Z, int cin, int cout, int ks, const int32_t *tiles, int n_tiles, int act, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * fp16-operand tensor-core path (tcgen05 kind::f16, fp32 accumulate): activations and weights are STORED as fp16 (same
+ * 11-bit significand TF32 keeps, half the bytes through L2 -- the kernel is bound by operand feed).  in16 is a dense VC
+ * fp16 tensor; w16 from sis3d_pack_conv_weight_tc_f16; outputs: out32 (fp32, may be NULL) and/or out16 (fp16 twin with
+ * the same row stride / channel offset, may be NULL).  cin % 64 == 0 uses 128-B rows, cin == 32 64-B rows.
+ * sis3d_cast_f16 makes the fp16 copy of an fp32 VC tensor; sis3d_conv3d_ex / sis3d_backproject_conv_k2s2_ex are the
+ * fp32 kernels with an optional fp16 twin output.
+ * ---------------------------------------------------------------------------------------------- */
+int sis3d_pack_conv_weight_tc_f16(const float *w_oidhw, int cout, int cin, int ks, uint16_t *w16, void *stream);
+int sis3d_cast_f16(const float *in, int in_ld, int in_coff, int64_t rows, int C, uint16_t *out, void *stream);
+int sis3d_conv3d_tc_f16(const uint16_t *in16, const uint16_t *w16, const float *bias, const float *residual,
+                        int res_ld, int res_coff, float *out32, uint16_t *out16, int out_ld, int out_coff, int X,
+                        int Y, int Z, int cin, int cout, int ks, const int32_t *tiles, int n_tiles, int act, void *stream);
+int sis3d_conv3d_ex(const float *in, int64_t in_chan_stride, const float *w_packed, const float *bias,
+                    const float *residual, int res_ld, int res_coff, float *out, uint16_t *out16, int out_ld,
+                    int out_coff, const sis3d_region *regions, int n_regions, int n_tiles, int cin, int cout, int ks,
+                    int stride, int pad, int act, void *stream);
+int sis3d_backproject_conv_k2s2_ex(const float *feats, float *feats_t, const int16_t *pix, const int32_t *pairs,
+                                   const int32_t *n_pairs, int n_views, int C, int img_w, int img_h, int X, int Y,
+                                   int Z, const float *w_packed, int cout, float *out, uint16_t *out16, int out_ld,
+                                   int out_coff, void *workspace, size_t workspace_bytes, void *stream);
+
 /* MaxPool3d(3,1,1) on a VC tensor (lib/nets/backbones.py:207,212,220); output row stride out_ld and
  * channel offset out_coff as for the convolution. */
 int sis3d_maxpool3(const float *in, float *out, int out_ld, int out_coff, int X, int Y, int Z, int C, void *stream);

@@ -471,3 +471,72 @@ def test_linear_tc_tf32(S, M, K, N, act):
     assert torch.equal(outs[0], outs[1])
     rel = ((outs[0] - ref).norm() / ref.norm()).item()
     assert rel < 2e-3, rel
+
+
+# ---------------------------------------------------------------- fp16-operand tensor-core conv (kind::f16)
+F16_CASES = [  # cin, cout, dims, bias, res, act, ks
+    (32, 32, (17, 9, 11), True, False, 1, 3), (32, 64, (24, 12, 24), True, True, 1, 1), (32, 32, (48, 24, 48), True, False, 1, 1),
+    (64, 64, (24, 12, 24), True, False, 1, 3), (64, 32, (11, 6, 9), True, False, 1, 1), (128, 128, (11, 6, 10), False, False, 1, 3),
+    (128, 256, (24, 12, 24), True, False, 1, 3), (64, 128, (7, 5, 6), True, True, 1, 1), (256, 128, (9, 4, 7), True, False, 0, 1)]
+
+
+@pytest.mark.parametrize("cin,cout,dims,bias,res,act,ks", F16_CASES)
+def test_conv3d_tc_f16_vs_fp32(S, cin, cout, dims, bias, res, act, ks):
+    """fp16-stored operands, fp32 accumulation: error bounded by the fp16 rounding of inputs/weights (2^-11 relative);
+    both the fp32 output and its fp16 twin are produced in one launch."""
+    rng = np.random.default_rng(cin * 7 + cout + dims[0])
+    x = rng.standard_normal((1, cin) + dims).astype(np.float32)
+    w = (rng.standard_normal((cout, cin, ks, ks, ks)) / np.sqrt(cin * ks ** 3)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32) if bias else None
+    ref = F.conv3d(torch.from_numpy(x), torch.from_numpy(w), None if b is None else torch.from_numpy(b), padding=ks // 2)
+    r = rng.standard_normal(tuple(ref.shape)).astype(np.float32) if res else None
+    if res:
+        ref = ref + torch.from_numpy(r)
+    if act == 1:
+        ref = F.relu(ref)
+    xd = torch.from_numpy(x[0]).to(DEV).permute(1, 2, 3, 0).contiguous()
+    x16 = torch.empty(dims + (cin,), dtype=torch.float16, device=DEV)
+    S.check(S.lib.sis3d_cast_f16(S.ptr(xd), cin, 0, C.c_int64(dims[0] * dims[1] * dims[2]), cin, S.ptr(x16), S.stream()))
+    assert torch.equal(x16, xd.half())
+    wdev = torch.from_numpy(w).to(DEV)
+    bdev = torch.from_numpy(b).to(DEV) if bias else None
+    w16 = torch.empty(cout, ks ** 3 * cin, dtype=torch.float16, device=DEV)
+    S.check(S.lib.sis3d_pack_conv_weight_tc_f16(S.ptr(wdev), cout, cin, ks, S.ptr(w16), S.stream()))
+    out = torch.full(dims + (cout + 4,), 7.0, device=DEV)
+    out16 = torch.full(dims + (cout + 4,), 7.0, dtype=torch.float16, device=DEV)
+    rd = torch.from_numpy(r[0]).to(DEV).permute(1, 2, 3, 0).contiguous() if res else None
+    S.check(S.lib.sis3d_conv3d_tc_f16(S.ptr(x16), S.ptr(w16), S.ptr(bdev), S.ptr(rd), cout if res else 0, 0, S.ptr(out), S.ptr(out16),
+                                      cout + 4, 4, *dims, cin, cout, ks, None, 0, act, S.stream()))
+    torch.cuda.synchronize()
+    got = out[..., 4:].permute(3, 0, 1, 2).cpu()
+    assert torch.all(out[..., :4] == 7.0) and torch.all(out16[..., :4] == 7.0)
+    rel = ((got - ref[0]).norm() / ref[0].norm()).item()
+    assert rel < 1.5e-3, f"rel {rel:.2e}"
+    assert torch.equal(out16[..., 4:], out[..., 4:].half())
+    # fp16-only output (no fp32 store)
+    out16b = torch.zeros(dims + (cout,), dtype=torch.float16, device=DEV)
+    S.check(S.lib.sis3d_conv3d_tc_f16(S.ptr(x16), S.ptr(w16), S.ptr(bdev), S.ptr(rd), cout if res else 0, 0, None, S.ptr(out16b),
+                                      cout, 0, *dims, cin, cout, ks, None, 0, act, S.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out16b, out[..., 4:].half())
+
+
+def test_simt_conv_and_sparse_fp16_twin(S):
+    rng = np.random.default_rng(12)
+    cin, cout, dims = 2, 32, (10, 8, 6)
+    x = rng.standard_normal((1, cin) + dims).astype(np.float32)
+    w = (rng.standard_normal((cout, cin, 2, 2, 2)) / 4).astype(np.float32)
+    od = tuple(d // 2 for d in dims)
+    xd, wd = torch.from_numpy(x).to(DEV), torch.from_numpy(w).to(DEV)
+    packed = torch.empty(8 * cin, cout, device=DEV)
+    S.check(S.lib.sis3d_pack_conv_weight(S.ptr(wd), cout, cin, 2, S.ptr(packed), S.stream()))
+    out = torch.zeros(od + (cout,), device=DEV)
+    out16 = torch.zeros(od + (cout,), dtype=torch.float16, device=DEV)
+    X, Y, Z = dims
+    regions, tiles = S.make_regions([dict(in_off=0, out_off=0, in_dim=dims, out_dim=od, in_stride=(Y * Z, Z, 1))], DEV)
+    S.check(S.lib.sis3d_conv3d_ex(S.ptr(xd), C.c_int64(X * Y * Z), S.ptr(packed), None, None, 0, 0, S.ptr(out), S.ptr(out16), cout, 0,
+                                  S.ptr(regions), 1, tiles, cin, cout, 2, 2, 0, 1, S.stream()))
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv3d(torch.from_numpy(x), torch.from_numpy(w), stride=2))[0].permute(1, 2, 3, 0)
+    torch.testing.assert_close(out.cpu(), ref, atol=2e-5, rtol=1e-4)
+    assert torch.equal(out16, out.half())
