@@ -28,11 +28,12 @@ from lib.utils.config import cfg
 
 class Act:
     """A voxel activation: tensor + spatial dims + channels; layout 'vc' ([X,Y,Z,C]) or 'ncdhw'."""
-    __slots__ = ("t", "dims", "C", "layout", "ld", "coff")
+    __slots__ = ("t", "dims", "C", "layout", "ld", "coff", "h")
 
-    def __init__(self, t, dims, Cn, layout="vc", ld=None, coff=0):
+    def __init__(self, t, dims, Cn, layout="vc", ld=None, coff=0, h=None):
         self.t, self.dims, self.C, self.layout = t, tuple(int(d) for d in dims), int(Cn), layout
         self.ld, self.coff = int(ld if ld is not None else Cn), int(coff)
+        self.h = h  # optional dense fp16 twin [X,Y,Z,C] (fp16-operand tensor-core mode); `t` may be None when only `h` exists
 
     @property
     def nvox(self):
@@ -66,7 +67,9 @@ class Network(nn.Module):
         self._const_cache = {}
         self._keep_debug = False
         self._packed_tc = {}
-        # conv math for the 3x3x3 layers: 'tf32' = tcgen05 tensor cores (default), 'fp32' = CUDA-core exact path
+        self._packed_h = {}
+        # conv math: 'tf32' = tcgen05 with fp32-stored operands (default), 'fp16' = tcgen05 with fp16-stored operands
+        # (same 11-bit significand, half the L2 traffic), 'fp32' = CUDA-core exact path
         self._math = os.environ.get("SIS3D_CONV_MATH", str(cfg.get("CONV_MATH", "tf32"))).lower()
         self._graphs = {}
         self._slots = []
@@ -157,7 +160,7 @@ class Network(nn.Module):
         self._pack_dirty = False
         if v == self._packed_version:
             return
-        self._packed, self._packed_tc = {}, {}
+        self._packed, self._packed_tc, self._packed_h = {}, {}, {}
         params = dict(self.named_parameters())
         for name, p in params.items():
             if not name.endswith(".weight"):
@@ -176,6 +179,10 @@ class Network(nn.Module):
                 wtc = torch.empty(cout, ks ** 3 * cin, dtype=torch.float32, device=w.device)
                 S.check(S.lib.sis3d_pack_conv_weight_tc(S.ptr(w), cout, cin, ks, S.ptr(wtc), S.stream()), "pack_tc")
                 self._packed_tc[base] = wtc
+                if cin % 64 == 0 or (cin == 32 and cout <= 64):
+                    w16 = torch.empty(cout, ks ** 3 * cin, dtype=torch.float16, device=w.device)
+                    S.check(S.lib.sis3d_pack_conv_weight_tc_f16(S.ptr(w), cout, cin, ks, S.ptr(w16), S.stream()), "pack_f16")
+                    self._packed_h[base] = w16
         for lvl in (1, 2, 3):  # both RPN heads of a level as ONE 1x1 conv: [2A | 6A] output channels, zero-padded to a
             # tensor-core friendly width (32/64/128k) so the merged head runs on the tcgen05 kernel as well
             c, b = f"rpn_cls_score_net_level{lvl}.0", f"rpn_bbox_pred_net_level{lvl}"
@@ -195,6 +202,9 @@ class Network(nn.Module):
                     wtc = torch.empty(cpad, cin, dtype=torch.float32, device=w.device)
                     S.check(S.lib.sis3d_pack_conv_weight_tc(S.ptr(wp), cpad, cin, 1, S.ptr(wtc), S.stream()), "pack_tc")
                     self._packed_tc[f"rpn_heads_level{lvl}"] = wtc
+                    w16 = torch.empty(cpad, cin, dtype=torch.float16, device=w.device)
+                    S.check(S.lib.sis3d_pack_conv_weight_tc_f16(S.ptr(wp), cpad, cin, 1, S.ptr(w16), S.stream()), "pack_f16")
+                    self._packed_h[f"rpn_heads_level{lvl}"] = w16
         torch.cuda.current_stream().synchronize()
         self._packed_version = v
 
@@ -224,8 +234,20 @@ class Network(nn.Module):
             self._region_cache[key] = hit
         return hit
 
+    def _half(self, x: Act):
+        """fp16 twin of an activation (cast once, cached on the Act)."""
+        if x.h is None:
+            x.h = torch.empty(*x.dims, x.C, dtype=torch.float16, device=x.t.device)
+            tok = self._rec("cast_f16")
+            S.check(S.lib.sis3d_cast_f16(S.ptr(x.t), x.ld, x.coff, C.c_int64(x.nvox), x.C, S.ptr(x.h), S.stream()), "cast_f16")
+            self._rec_end(tok)
+        return x.h
+
     def _conv(self, x: Act, name, stride=1, pad=None, act=0, residual: Act = None, out: Act = None,
-              regions=None, out_dims=None):
+              regions=None, out_dims=None, want32=True, want16=False, out16=None):
+        """One convolution.  Dispatch: tcgen05 fp16-operand kernel ('fp16' math), tcgen05 TF32 kernel ('tf32'), else the
+        fp32 CUDA-core kernel.  want32/want16 choose which of the fp32 output / dense fp16 twin are produced (the twin
+        feeds the next tensor-core layer in 'fp16' math); out16 = caller-provided fp16 destination (ragged mask stage)."""
         packed, bias, cout, cin, ks = self._packed[name]
         if cin != x.C:
             raise S.Sis3dError(f"{name}: expected {cin} input channels, got {x.C}")
@@ -234,32 +256,50 @@ class Network(nn.Module):
         if out_dims is None:
             out_dims = tuple(d // 2 for d in x.dims) if stride == 2 else x.dims
         regions_given = regions
-        if regions is None:
-            regions, n_tiles = self._regions_single(x, out_dims, stride)
-        else:
-            regions, n_tiles = regions
+        dev = (x.t if x.t is not None else x.h).device
+        f16 = self._math == "fp16"
+        tc_ok = (regions_given is None and stride == 1 and pad == (1 if ks == 3 else 0) and x.layout == "vc"
+                 and x.ld == x.C and x.coff == 0 and act in (0, 1))
+        if not f16:
+            want32, want16 = True, False
         if out is None:
-            out = Act(torch.empty(*out_dims, cout, dtype=torch.float32, device=x.t.device), out_dims, cout)
-        if (self._math == "tf32" and regions_given is None and name in self._packed_tc and stride == 1
-                and pad == (1 if ks == 3 else 0) and x.layout == "vc" and x.ld == x.C and x.coff == 0 and act in (0, 1)):
+            t32 = torch.empty(*out_dims, cout, dtype=torch.float32, device=dev) if want32 else None
+            out = Act(t32, out_dims, cout)
+        twin_ok = out.ld == cout and out.coff == 0  # the twin shares the geometry of the fp32 output
+        if want16 and twin_ok and out16 is None:
+            out.h = torch.empty(*out_dims, cout, dtype=torch.float16, device=dev)
+        h_ptr = S.ptr(out16) if out16 is not None else (S.ptr(out.h) if (want16 and twin_ok) else None)
+        res_args = (S.ptr(residual.t) if residual is not None else None, residual.ld if residual is not None else 0,
+                    residual.coff if residual is not None else 0)
+        if f16 and tc_ok and name in self._packed_h:
+            tok = self._rec(f"conv_tc16[{name}]")
+            S.check(S.lib.sis3d_conv3d_tc_f16(S.ptr(self._half(x)), S.ptr(self._packed_h[name]), S.ptr(bias), *res_args,
+                                              S.ptr(out.t) if out.t is not None else None, h_ptr, out.ld, out.coff, *x.dims,
+                                              cin, cout, ks, None, 0, act, S.stream()), f"conv3d_tc_f16[{name}]")
+            self._rec_end(tok)
+            return out
+        if x.t is None:
+            raise S.Sis3dError(f"{name}: this layer needs the fp32 activation but only the fp16 twin was produced")
+        if out.t is None and h_ptr is None:
+            out.t = torch.empty(*out_dims, cout, dtype=torch.float32, device=dev)
+        if self._math in ("tf32", "fp16") and tc_ok and name in self._packed_tc and out.t is not None and h_ptr is None:
             tok = self._rec(f"conv_tc[{name}]")
-            S.check(S.lib.sis3d_conv3d_k3_tc(S.ptr(x.t), S.ptr(self._packed_tc[name]), S.ptr(bias),
-                                             S.ptr(residual.t) if residual is not None else None,
-                                             residual.ld if residual is not None else 0,
-                                             residual.coff if residual is not None else 0,
+            S.check(S.lib.sis3d_conv3d_k3_tc(S.ptr(x.t), S.ptr(self._packed_tc[name]), S.ptr(bias), *res_args,
                                              S.ptr(out.t), out.ld, out.coff, *x.dims, cin, cout, ks, None, 0, act, S.stream()),
                     f"conv3d_k3_tc[{name}]")
             self._rec_end(tok)
             return out
+        if regions is None:
+            regions, n_tiles = self._regions_single(x, out_dims, stride)
+        else:
+            regions, n_tiles = regions
         in_sc = 1 if x.layout == "vc" else x.nvox
         xin = x.t if x.coff == 0 else x.t.reshape(-1)[x.coff:]
         tok = self._rec(f"conv[{name}]")
-        S.check(S.lib.sis3d_conv3d(S.ptr(xin), C.c_int64(in_sc), S.ptr(packed), S.ptr(bias),
-                                   S.ptr(residual.t) if residual is not None else None,
-                                   residual.ld if residual is not None else 0,
-                                   residual.coff if residual is not None else 0,
-                                   S.ptr(out.t), out.ld, out.coff, S.ptr(regions), regions.numel() // S.REGION_BYTES,
-                                   n_tiles, cin, cout, ks, stride, pad, act, S.stream()), f"conv3d[{name}]")
+        S.check(S.lib.sis3d_conv3d_ex(S.ptr(xin), C.c_int64(in_sc), S.ptr(packed), S.ptr(bias), *res_args,
+                                      S.ptr(out.t) if out.t is not None else None, h_ptr, out.ld, out.coff, S.ptr(regions),
+                                      regions.numel() // S.REGION_BYTES, n_tiles, cin, cout, ks, stride, pad, act, S.stream()),
+                f"conv3d[{name}]")
         self._rec_end(tok)
         return out
 
@@ -286,10 +326,12 @@ class Network(nn.Module):
         return y
 
     def _bottleneck(self, x: Act, name, out: Act = None):
-        """1x1 -> relu -> 3x3x3 -> relu -> 1x1 (+x) -> relu  (reference: backbones.py:28-40)."""
-        y = self._conv(x, name + ".conv1", act=1)
-        y = self._conv(y, name + ".conv2", act=1)
-        return self._conv(y, name + ".conv3", act=1, residual=x, out=out)
+        """1x1 -> relu -> 3x3x3 -> relu -> 1x1 (+x) -> relu  (reference: backbones.py:28-40).  In 'fp16' math the two inner
+        activations exist only as fp16 (they feed tensor-core layers only); the block output is fp32 (+ fp16 twin when it
+        is a dense tensor, for the next block's first conv)."""
+        y = self._conv(x, name + ".conv1", act=1, want32=False, want16=True)
+        y = self._conv(y, name + ".conv2", act=1, want32=False, want16=True)
+        return self._conv(y, name + ".conv3", act=1, residual=x, out=out, want32=True, want16=True)
 
     def _pool(self, x: Act, out: Act = None):
         if out is None:
@@ -307,9 +349,9 @@ class Network(nn.Module):
         for i, op in enumerate(spec):
             dst = final_out(x, op) if (final_out is not None and i == len(spec) - 1) else None
             if op[0] == "k2s2":
-                x = self._conv(x, f"{prefix}.{op[1]}", stride=2, pad=0, act=1, out=dst)
+                x = self._conv(x, f"{prefix}.{op[1]}", stride=2, pad=0, act=1, out=dst, want16=True)
             elif op[0] == "k3":
-                x = self._conv(x, f"{prefix}.{op[1]}", act=1, out=dst)
+                x = self._conv(x, f"{prefix}.{op[1]}", act=1, out=dst, want16=True)
             elif op[0] == "bneck":
                 x = self._bottleneck(x, f"{prefix}.{op[1]}", out=dst)
             elif op[0] == "pool":
@@ -373,14 +415,17 @@ class Network(nn.Module):
             packed, _, cout, cin, _ = self._packed[f"color.{first[1]}"]
             od = tuple(d // 2 for d in dims)
             out = Act(torch.empty(*od, cout, dtype=torch.float32, device=dev), od, cout)
+            if self._math == "fp16":
+                out.h = torch.empty(*od, cout, dtype=torch.float16, device=dev)
             feats = feats.contiguous()
             feats_t = torch.empty(feats.shape[0], w * h, feats.shape[1], dtype=torch.float32, device=dev)
             nbytes = int(S.lib.sis3d_backproject_conv_k2s2_workspace_bytes(*dims, cout))
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             tok = self._rec("backproject_conv_k2s2")
-            S.check(S.lib.sis3d_backproject_conv_k2s2(S.ptr(feats), S.ptr(feats_t), S.ptr(pix), S.ptr(pairs), S.ptr(n_pairs),
-                                                      feats.shape[0], feats.shape[1], w, h, *dims, S.ptr(packed), cout,
-                                                      S.ptr(out.t), out.ld, 0, S.ptr(ws), C.c_size_t(nbytes), S.stream()),
+            S.check(S.lib.sis3d_backproject_conv_k2s2_ex(S.ptr(feats), S.ptr(feats_t), S.ptr(pix), S.ptr(pairs), S.ptr(n_pairs),
+                                                         feats.shape[0], feats.shape[1], w, h, *dims, S.ptr(packed), cout,
+                                                         S.ptr(out.t), S.ptr(out.h), out.ld, 0, S.ptr(ws), C.c_size_t(nbytes),
+                                                         S.stream()),
                     "backproject_conv_k2s2")
             self._rec_end(tok)
             return ("color0", out)
@@ -437,7 +482,7 @@ class Network(nn.Module):
     def _region_proposal(self, feats, dims, out=None):
         """reference: network.py:537-587 + 657-683 (softmax/anchors/decode/top-N/NMS fused on device)."""
         def head(lvl, f, A):
-            h = self._conv(f, f"rpn_net_level{lvl}", act=1)
+            h = self._conv(f, f"rpn_net_level{lvl}", act=1, want32=False, want16=True)  # hidden feeds only the merged head
             heads = self._conv(h, f"rpn_heads_level{lvl}")  # [N, ld]: [2A class logits | 6A box deltas | zero pad]
             heads.t.record_stream(torch.cuda.current_stream())
             return heads
@@ -510,7 +555,7 @@ class Network(nn.Module):
         dev = scene_ncdhw.device
         X, Y, Z = (int(v) for v in scene_ncdhw.shape[2:])
         ncls = self._packed["mask_backbone.geometry.10"][2]
-        use_tc = self._math == "tf32" and "mask_backbone.geometry.2" in self._packed_tc
+        use_tc = self._math in ("tf32", "fp16") and "mask_backbone.geometry.2" in self._packed_tc
         det_host = np.ascontiguousarray(det_host[:n], dtype=np.float32)
         plan = S.MaskPlan()
         cap = self._arena["mask_tables_host"].numel() if "mask_tables_host" in self._arena else 1 << 18
@@ -544,20 +589,42 @@ class Network(nn.Module):
             n_tiles = int(plan.n_tiles_tc)
             r_tiles = tables[plan.off_rest:plan.off_rest + 32 * n_tiles]
             cvox = Xc * Yc * Zc
-            canv = self._ws("mask_canvas", 2 * cvox * 64, torch.float32, dev)
-            canv.zero_()
-            bufs = [canv[:cvox * 64], canv[cvox * 64:]]
-            x = self._conv(scene, "mask_backbone.geometry.0", act=1, regions=(r_first, t_first), out_dims=(Xc, Yc, Zc),
-                           out=Act(bufs[0], (Xc, Yc, Zc), 64))
-            for li, idx in enumerate((2, 4, 6, 8)):
-                name = f"mask_backbone.geometry.{idx}"
-                dst = Act(bufs[(li + 1) % 2], (Xc, Yc, Zc), 64)
-                tok = self._rec(f"conv_tc[{name}]")
-                S.check(S.lib.sis3d_conv3d_k3_tc(S.ptr(x.t), S.ptr(self._packed_tc[name]), None, None, 0, 0, S.ptr(dst.t), 64,
-                                                 0, Xc, Yc, Zc, 64, 64, 3, S.ptr(r_tiles), n_tiles, 1, S.stream()),
-                        f"conv3d_k3_tc[{name}]")
-                self._rec_end(tok)
-                x = dst
+            if self._math == "fp16" and "mask_backbone.geometry.2" in self._packed_h:
+                # fp16 canvases between the layers (zeroed: the slabs between crops are the zero padding); the last
+                # 3x3x3 layer writes fp32 for the 1x1 head, which reads crop voxels only (no zeroing needed)
+                c16 = self._ws("mask_canvas16", 2 * cvox * 64, torch.float16, dev)
+                c16.zero_()
+                h = [c16[:cvox * 64], c16[cvox * 64:]]
+                c32 = self._ws("mask_canvas32", cvox * 64, torch.float32, dev)
+                self._conv(scene, "mask_backbone.geometry.0", act=1, regions=(r_first, t_first), out_dims=(Xc, Yc, Zc),
+                           out=Act(None, (Xc, Yc, Zc), 64), out16=h[0])
+                cur = 0
+                for idx in (2, 4, 6, 8):
+                    name = f"mask_backbone.geometry.{idx}"
+                    last3 = idx == 8
+                    tok = self._rec(f"conv_tc16[{name}]")
+                    S.check(S.lib.sis3d_conv3d_tc_f16(S.ptr(h[cur]), S.ptr(self._packed_h[name]), None, None, 0, 0,
+                                                      S.ptr(c32) if last3 else None, None if last3 else S.ptr(h[1 - cur]), 64, 0,
+                                                      Xc, Yc, Zc, 64, 64, 3, S.ptr(r_tiles), n_tiles, 1, S.stream()),
+                            f"conv3d_tc_f16[{name}]")
+                    self._rec_end(tok)
+                    cur = 1 - cur
+                x = Act(c32, (Xc, Yc, Zc), 64)
+            else:
+                canv = self._ws("mask_canvas", 2 * cvox * 64, torch.float32, dev)
+                canv.zero_()
+                bufs = [canv[:cvox * 64], canv[cvox * 64:]]
+                x = self._conv(scene, "mask_backbone.geometry.0", act=1, regions=(r_first, t_first), out_dims=(Xc, Yc, Zc),
+                               out=Act(bufs[0], (Xc, Yc, Zc), 64))
+                for li, idx in enumerate((2, 4, 6, 8)):
+                    name = f"mask_backbone.geometry.{idx}"
+                    dst = Act(bufs[(li + 1) % 2], (Xc, Yc, Zc), 64)
+                    tok = self._rec(f"conv_tc[{name}]")
+                    S.check(S.lib.sis3d_conv3d_k3_tc(S.ptr(x.t), S.ptr(self._packed_tc[name]), None, None, 0, 0, S.ptr(dst.t), 64,
+                                                     0, Xc, Yc, Zc, 64, 64, 3, S.ptr(r_tiles), n_tiles, 1, S.stream()),
+                            f"conv3d_k3_tc[{name}]")
+                    self._rec_end(tok)
+                    x = dst
         else:
             r_mid, t_mid = tables[plan.off_rest:plan.off_rest + rb], int(plan.tiles_mid)
             act_buf = self._ws("mask_act", 2 * total * 64, torch.float32, dev)
