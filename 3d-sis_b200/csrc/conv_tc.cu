@@ -510,10 +510,10 @@ extern "C" int sis3d_conv3d_tc_f16(const uint16_t *in16, const uint16_t *w16, co
     if ((out_ld | out_coff | res_ld | res_coff) & 3) return SIS3D_EINVAL;
     EncodeTiledFn enc = get_encode();
     if (!enc) return SIS3D_EUNSUPPORTED;
-    const int BN = cout >= 128 ? 128 : cout;
     const bool wide = cin % 64 == 0;       // 64 channels = 128 B rows; C_in = 32 -> 64 B rows (SWIZZLE_64B)
+    const int BN = wide ? (cout >= 128 ? 128 : cout) : (cout >= 64 ? 64 : cout);  // 64-B rows: N tiles of at most 64
     const int kc = wide ? 64 : 32;
-    if (!wide && BN == 128) return SIS3D_EUNSUPPORTED;
+    if (!wide && cin != 32) return SIS3D_EUNSUPPORTED;
     const CUtensorMapSwizzle sw = wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUtensorMap tmA, tmB;
     {

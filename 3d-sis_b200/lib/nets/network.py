@@ -179,7 +179,7 @@ class Network(nn.Module):
                 wtc = torch.empty(cout, ks ** 3 * cin, dtype=torch.float32, device=w.device)
                 S.check(S.lib.sis3d_pack_conv_weight_tc(S.ptr(w), cout, cin, ks, S.ptr(wtc), S.stream()), "pack_tc")
                 self._packed_tc[base] = wtc
-                if cin % 64 == 0 or (cin == 32 and cout <= 64):
+                if cin % 64 == 0 or cin == 32:
                     w16 = torch.empty(cout, ks ** 3 * cin, dtype=torch.float16, device=w.device)
                     S.check(S.lib.sis3d_pack_conv_weight_tc_f16(S.ptr(w), cout, cin, ks, S.ptr(w16), S.stream()), "pack_f16")
                     self._packed_h[base] = w16

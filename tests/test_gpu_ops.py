@@ -477,7 +477,8 @@ def test_linear_tc_tf32(S, M, K, N, act):
 F16_CASES = [  # cin, cout, dims, bias, res, act, ks
     (32, 32, (17, 9, 11), True, False, 1, 3), (32, 64, (24, 12, 24), True, True, 1, 1), (32, 32, (48, 24, 48), True, False, 1, 1),
     (64, 64, (24, 12, 24), True, False, 1, 3), (64, 32, (11, 6, 9), True, False, 1, 1), (128, 128, (11, 6, 10), False, False, 1, 3),
-    (128, 256, (24, 12, 24), True, False, 1, 3), (64, 128, (7, 5, 6), True, True, 1, 1), (256, 128, (9, 4, 7), True, False, 0, 1)]
+    (128, 256, (24, 12, 24), True, False, 1, 3), (64, 128, (7, 5, 6), True, True, 1, 1), (256, 128, (9, 4, 7), True, False, 0, 1),
+    (32, 128, (8, 8, 8), True, True, 1, 1)]
 
 
 @pytest.mark.parametrize("cin,cout,dims,bias,res,act,ks", F16_CASES)
