@@ -873,13 +873,14 @@ class Network(nn.Module):
         from collections import deque
         q = deque()
         i = 0
+        depth = max(2, int(os.environ.get("SIS3D_PIPE_DEPTH", "3")))  # scenes in flight (= stream slots)
         for blobs in blobs_iter:
-            q.append([blobs, self._submit(blobs, None, self._slot(1 + i % 3)), False])
+            q.append([blobs, self._submit(blobs, None, self._slot(1 + i % depth)), False])
             i += 1
             if len(q) >= 2 and not q[-2][2]:
                 self._launch_ragged(q[-2][1])
                 q[-2][2] = True
-            if len(q) == 3:
+            if len(q) == depth:
                 b, h, _ = q.popleft()
                 yield b, self._finalize(h)
         while q:
