@@ -2,15 +2,17 @@
 //
 //   D[128 voxels x BN] (TMEM, fp32)  +=  A[128 x 32] (smem, TF32)  x  B[BN x 32]^T (smem, TF32)
 //
-// * M tile = an 8x4x4 brick of output voxels.  For every filter tap (27) and every 32-channel slice of
-//   C_in, ONE 4-D TMA box {32 ch, 4 z, 4 y, 8 x} fetches the shifted input brick straight from the VC
-//   activation tensor; voxels outside the volume are zero-filled by the TMA unit, which *is* the
-//   convolution's zero padding -- no halo logic, no im2col buffer.  Rows land 128 B apart in the
-//   canonical K-major SWIZZLE_128B layout tcgen05.mma consumes.
-// * B tile = BN rows of the weight matrix W[C_out][27*C_in] (k = tap*C_in + c), 2-D TMA, same swizzle.
+// * M tile = an 8x2x8 (x,y,z) brick of output voxels, rows ordered z (8 rows = one swizzle atom), y, x.  For every
+//   (dy, dz) tap pair (9) and every 32-channel slice of C_in, ONE 4-D TMA box {32 ch, 8 z, 2 y, 10 x} fetches the
+//   shifted input slab -- with a one-plane halo in x -- straight from the VC activation tensor; the three x-taps then
+//   read rows [16 dx, 16 dx + 128) of that slab, an offset of two whole swizzle atoms, so the descriptor just moves by
+//   2 KB: A traffic is 9 x 1.25 instead of 27 bricks per K slice (2.4x less).  Voxels outside the volume are zero-filled
+//   by the TMA unit, which *is* the convolution's zero padding -- no halo logic, no im2col buffer.  Rows land 128 B
+//   apart in the canonical K-major SWIZZLE_128B layout tcgen05.mma consumes.
+// * B tiles = BN rows of the weight matrix W[C_out][27*C_in] (k = tap*C_in + c) for the three x-taps, 2-D TMA, same swizzle.
 // * Warp roles (128 threads): thread 0 = TMA producer, thread 32 = MMA issuer (tcgen05.mma
-//   kind::tf32, cta_group::1, M=128, N=BN, K=8 x4 per stage), all four warps = epilogue
-//   (tcgen05.ld 32x32b -> bias / residual / ReLU -> global).  4-stage full/empty mbarrier ring;
+//   kind::tf32, cta_group::1, M=128, N=BN, K=8; 3 x-taps x 4 per stage), all four warps = epilogue
+//   (tcgen05.ld 32x32b -> bias / residual / ReLU -> global).  3-stage full/empty mbarrier ring;
 //   tcgen05.commit releases smem slots and signals the accumulator.
 // * Tiles may be listed explicitly (ragged RoI crops packed on one zero-separated canvas, mask head)
 //   or implied by the volume.
@@ -23,7 +25,7 @@
 
 namespace sis3d {
 
-constexpr int TC_BX = 8, TC_BY = 4, TC_BZ = 4;
+constexpr int TC_BX = 8, TC_BY = 2, TC_BZ = 8;  // 128 voxels; rows ordered z (8 = one swizzle atom), y, x
 constexpr int TC_BM = TC_BX * TC_BY * TC_BZ;  // 128
 constexpr int TC_KC = 32;                      // channels per stage: 32 * 4 B = 128 B = one swizzle row
 constexpr int TC_STAGES_MAX = 4;
@@ -120,6 +122,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
 // ~1.3-1.5 waves at two CTAs/SM)
 template <int BN>
 struct TcStages { static constexpr int value = BN >= 128 ? 4 : 3; };
+// stage count per kernel flavour: the 3x3x3 stages are 3x bigger (slab + three weight tiles)
+template <int BN, int KS, int ROWB>
+struct TcStagesOf { static constexpr int value = KS == 3 ? 3 : TcStages<BN>::value; };
+template <int BN, int KS, int ROWB>
+constexpr size_t tc_smem_bytes() {
+    return (size_t)TcStagesOf<BN, KS, ROWB>::value *
+               ((KS == 3 ? (TC_BX + 2) * TC_BY * TC_BZ : TC_BM) * ROWB + (KS == 3 ? 3 : 1) * BN * ROWB) + 1024 + 256;
+}
 
 // EB = operand element bytes: 4 -> fp32 storage, kind::tf32;  2 -> fp16 storage, kind::f16 (same 11-bit significand,
 // half the operand bytes through L2).  ROWB = bytes of one K slice row in shared memory (128, or 64 for C_in = 32 in fp16).
@@ -127,10 +137,14 @@ template <int BN, int KS, int EB = 4, int ROWB = 128>
 __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
     constexpr int KC = ROWB / EB;            // channels per pipeline stage
-    constexpr int A_BYTES = TC_BM * ROWB;
+    // 3x3x3: one stage = one (dy, dz) pair: an x-halo slab of (8+2) x-planes (160 rows) serves the three x-taps --
+    // tap dx reads rows [dx*16, dx*16+128), a whole-swizzle-atom offset -- plus the three taps' weight tiles.
+    constexpr int XT = KS == 3 ? 3 : 1;      // x-taps per stage
+    constexpr int A_ROWS = KS == 3 ? (TC_BX + 2) * TC_BY * TC_BZ : TC_BM;
+    constexpr int A_BYTES = A_ROWS * ROWB;
     constexpr int B_BYTES = BN * ROWB;
-    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr int TC_STAGES = TcStages<BN>::value;
+    constexpr int STAGE_BYTES = A_BYTES + XT * B_BYTES;
+    constexpr int TC_STAGES = TcStagesOf<BN, KS, ROWB>::value;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B needs 1024 B alignment
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + TC_STAGES * STAGE_BYTES);
@@ -168,8 +182,7 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
     }
     const int n0 = blockIdx.y * BN;
     const int kchunks = a.cin / KC;
-    constexpr int TAPS = KS == 0 ? 1 : KS * KS * KS;  // 27 (3x3x3, pad 1) or 1 (1x1x1 / GEMM)
-    constexpr int SHIFT = KS == 3 ? 1 : 0;
+    constexpr int TAPS = KS == 3 ? 9 : 1;  // pipeline steps per K slice: 9 (dy,dz) pairs for 3x3x3, else 1
     int total = TAPS * kchunks, chunk0 = 0;
     if constexpr (KS == 0) {  // split-K GEMM: this CTA owns K chunks [chunk0, chunk0 + total)
         chunk0 = blockIdx.z * a.gemm_chunks_per_split;
@@ -185,14 +198,19 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
             mbar_wait(empty + s, ph ^ 1);
             mbar_expect_tx(full + s, STAGE_BYTES);
             const int tap = it / kchunks, kc = it - tap * kchunks;
-            const int dx = tap / (KS * KS), dy = (tap / KS) % KS, dz = tap % KS;
             uint8_t *sa = smem + s * STAGE_BYTES;
             if constexpr (KS == 0) {
                 tma_load_2d(sa, &tmA, full + s, (chunk0 + it) * KC, x0);
                 tma_load_2d(sa + A_BYTES, &tmB, full + s, (chunk0 + it) * KC, n0);
+            } else if constexpr (KS == 1) {
+                tma_load_4d(sa, &tmA, full + s, kc * KC, z0, y0, x0);
+                tma_load_2d(sa + A_BYTES, &tmB, full + s, kc * KC, n0);
             } else {
-                tma_load_4d(sa, &tmA, full + s, kc * KC, z0 + dz - SHIFT, y0 + dy - SHIFT, x0 + dx - SHIFT);
-                tma_load_2d(sa + A_BYTES, &tmB, full + s, tap * a.cin + kc * KC, n0);
+                const int dy = tap / 3, dz = tap % 3;  // tap = (dy, dz) pair; the slab covers x0-1 .. x0+8
+                tma_load_4d(sa, &tmA, full + s, kc * KC, z0 + dz - 1, y0 + dy - 1, x0 - 1);
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx)  // weight rows k = ((dx*3+dy)*3+dz)*C_in + c
+                    tma_load_2d(sa + A_BYTES + dx * B_BYTES, &tmB, full + s, ((dx * 3 + dy) * 3 + dz) * a.cin + kc * KC, n0);
             }
         }
     } else if (threadIdx.x == 32) {
@@ -208,9 +226,15 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
 #pragma unroll
-            for (int k = 0; k < ROWB / 32; ++k) {  // one MMA consumes 32 B of K (8 tf32 / 16 f16): advance inside the swizzle atom
-                if constexpr (EB == 4) umma_tf32(tmem_base, umma_desc<ROWB>(sa + k * 32), umma_desc<ROWB>(sb + k * 32), idesc, (it | k) ? 1u : 0u);
-                else umma_f16(tmem_base, umma_desc<ROWB>(sa + k * 32), umma_desc<ROWB>(sb + k * 32), idesc, (it | k) ? 1u : 0u);
+            for (int dx = 0; dx < XT; ++dx) {
+                // x-tap dx: A rows start 16 rows (= two 8-row swizzle atoms) further into the slab
+                const uint32_t ax = sa + dx * (TC_BY * TC_BZ) * ROWB, bx = sb + dx * B_BYTES;
+#pragma unroll
+                for (int k = 0; k < ROWB / 32; ++k) {  // one MMA consumes 32 B of K (8 tf32 / 16 f16): advance inside the swizzle atom
+                    const uint32_t acc = (it | dx | k) ? 1u : 0u;
+                    if constexpr (EB == 4) umma_tf32(tmem_base, umma_desc<ROWB>(ax + k * 32), umma_desc<ROWB>(bx + k * 32), idesc, acc);
+                    else umma_f16(tmem_base, umma_desc<ROWB>(ax + k * 32), umma_desc<ROWB>(bx + k * 32), idesc, acc);
+                }
             }
             umma_commit(empty + s);  // frees the smem slot once these MMAs retire
         }
@@ -244,7 +268,7 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
     mbar_wait(acc_ready, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int r = threadIdx.x;
-    const int vz = z0 + (r & 3), vy = y0 + ((r >> 2) & 3), vx = x0 + (r >> 4);
+    const int vz = z0 + (r & (TC_BZ - 1)), vy = y0 + ((r / TC_BZ) % TC_BY), vx = x0 + r / (TC_BZ * TC_BY);
     const bool valid = vx < x1 && vy < y1 && vz < z1;
     const int64_t vox = ((int64_t)vx * a.Y + vy) * a.Z + vz;
     float *orow = a.out ? a.out + vox * a.out_ld + a.out_coff + n0 : nullptr;
@@ -321,7 +345,7 @@ static EncodeTiledFn get_encode() {
 
 template <int BN, int KS, int EB = 4, int ROWB = 128>
 static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcArgs &a, int n_tiles, cudaStream_t s) {
-    const size_t smem = (size_t)TcStages<BN>::value * (TC_BM * ROWB + BN * ROWB) + 1024 + 256;
+    const size_t smem = tc_smem_bytes<BN, KS, ROWB>();
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(conv3d_k3_tc_kernel<BN, KS, EB, ROWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -388,7 +412,7 @@ extern "C" int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const floa
     {
         cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X};
         cuuint64_t strides[3] = {(cuuint64_t)cin * 4, (cuuint64_t)Z * cin * 4, (cuuint64_t)Y * Z * cin * 4};
-        cuuint32_t box[4] = {TC_KC, TC_BZ, TC_BY, TC_BX};
+        cuuint32_t box[4] = {TC_KC, TC_BZ, TC_BY, (cuuint32_t)(ks == 3 ? TC_BX + 2 : TC_BX)};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -519,7 +543,7 @@ extern "C" int sis3d_conv3d_tc_f16(const uint16_t *in16, const uint16_t *w16, co
     {
         cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X};
         cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)Z * cin * 2, (cuuint64_t)Y * Z * cin * 2};
-        cuuint32_t box[4] = {(cuuint32_t)kc, TC_BZ, TC_BY, TC_BX};
+        cuuint32_t box[4] = {(cuuint32_t)kc, TC_BZ, TC_BY, (cuuint32_t)(ks == 3 ? TC_BX + 2 : TC_BX)};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void *)in16, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)

@@ -158,7 +158,7 @@ int sis3d_mlp_tail(const float *x1, int R, int d1, const float *w2, const float 
  * Tensor-core path for the stride-1 layers, ks = 3 (pad 1) or ks = 1 (same call sites as sis3d_conv3d):
  * tcgen05.mma kind::tf32 with fp32 accumulation in TMEM, operands staged by 4-D/2-D TMA boxes
  * (csrc/conv_tc.cu).  `in` is a dense VC tensor [X][Y][Z][cin]; w_tc comes from
- * sis3d_pack_conv_weight_tc ([cout][ks^3*cin]).  tiles == NULL covers the whole volume with 8x4x4
+ * sis3d_pack_conv_weight_tc ([cout][ks^3*cin]).  tiles == NULL covers the whole volume with 8x2x8 (x,y,z)
  * bricks; otherwise tiles int32[n_tiles][8] = {x0,y0,z0,x1,y1,z1,0,0} lists brick origins and the
  * exclusive end of the voxels to be written (ragged RoI crops packed on one canvas).
  * Requires cin % 32 == 0 and cout in {32, 64, 128k}; returns SIS3D_EUNSUPPORTED otherwise.

@@ -401,9 +401,9 @@ def test_conv3d_tc_tile_list(S):
     w = (rng.standard_normal((cout, cin, 3, 3, 3)) / np.sqrt(cin * 27)).astype(np.float32)
     tiles = []
     for (x0, c), s in zip(crops, sizes):
-        for bx in range(0, s[0], 8):
-            for by in range(0, s[1], 4):
-                for bz in range(0, s[2], 4):
+        for bx in range(0, s[0], 8):  # 8x2x8 bricks (csrc/conv_tc.cu)
+            for by in range(0, s[1], 2):
+                for bz in range(0, s[2], 8):
                     tiles.append([x0 + bx, by, bz, x0 + s[0], s[1], s[2], 0, 0])
     td = torch.tensor(tiles, dtype=torch.int32, device=DEV)
     wtc = torch.empty(cout, 27 * cin, device=DEV)
