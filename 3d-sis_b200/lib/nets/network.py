@@ -53,6 +53,34 @@ def _declare(root, dotted, shape, fan_in):
     mod.register_parameter(parts[-1], nn.Parameter(torch.empty(shape).uniform_(-bound, bound), requires_grad=False))
 
 
+class _MaskList:
+    """Sequence of per-RoI mask tensors [1, num_classes, w, h, l] (the reference's `mask_pred[i]` list,
+    lib/nets/network.py:303-317) as lazily created views of the packed [total_voxels, num_classes] output."""
+
+    def __init__(self, packed, offs, sizes, ncls):
+        self.packed, self.offs, self.sizes, self.ncls = packed, offs, sizes, ncls
+
+    def __len__(self):
+        return len(self.sizes)
+
+    def __getitem__(self, j):
+        if isinstance(j, slice):
+            return [self[i] for i in range(*j.indices(len(self)))]
+        if j < 0:
+            j += len(self)
+        if not 0 <= j < len(self):
+            raise IndexError(j)
+        w, h, l = (int(v) for v in self.sizes[j])
+        m = self.packed[int(self.offs[j]) * self.ncls:int(self.offs[j + 1]) * self.ncls].view(w, h, l, self.ncls)
+        return m.permute(3, 0, 1, 2).unsqueeze(0)  # view in the reference layout
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def __eq__(self, other):
+        return list(self) == other if isinstance(other, list) else NotImplemented
+
+
 class Network(nn.Module):
     # layer programs of the concrete backbones are provided by subclasses (lib/nets/backbones.py)
     SPEC = None
@@ -446,10 +474,14 @@ class Network(nn.Module):
         out = [None] * len(fns)
         for st in side:
             st.wait_stream(cur)
-        for i, st in enumerate(side, 1):
-            with torch.cuda.stream(st):
-                out[i] = fns[i]()
-        out[0] = fns[0]()
+        pin = S.pin_stream(None)  # launches must follow torch's current stream inside the branches
+        try:
+            for i, st in enumerate(side, 1):
+                with torch.cuda.stream(st):
+                    out[i] = fns[i]()
+            out[0] = fns[0]()
+        finally:
+            S.pin_stream(pin)
         for st in side:
             cur.wait_stream(st)
         return out
@@ -642,18 +674,18 @@ class Network(nn.Module):
                                         S.f32(cfg.MASK_THRESH), None, S.ptr(bits), S.stream()), "mask_select")
         if extras is not None:
             extras.update(mask_bits=bits, mask_offsets=offs, mask_sizes=sizes)
-        masks = []
-        for j in range(nk):
-            w_, h_, l_ = (int(v) for v in sizes[j])
-            m = y.t[int(offs[j]) * ncls:int(offs[j + 1]) * ncls].view(w_, h_, l_, ncls)
-            masks.append(m.permute(3, 0, 1, 2).unsqueeze(0))  # [1,ncls,w,h,l] view, reference layout
-        return masks
+        return _MaskList(y.t, offs, sizes, ncls)
 
     # ------------------------------------------------------------------ forward
+    _carve_layouts = {}
+
     @staticmethod
     def _carve(pack, R, nc):
         """Typed views of the packed result buffer of the static stage (one buffer -> one clone / one copy)."""
-        o, out = 0, {}
+        lay = Network._carve_layouts.get((R, nc))
+        if lay is not None and pack.device.type != "meta":
+            return {name: pack[a:b].view(dt).view(shape) for name, a, b, dt, shape in lay[0]}, lay[1]
+        o, out, rec = 0, {}, []
         for name, shape, dt in (("rois", (R, 6), torch.float32), ("scores", (R,), torch.float32), ("level_ids", (R,), torch.int32),
                                 ("num", (4,), torch.int32), ("cls_score", (R, nc), torch.float32),
                                 ("bbox_pred", (R, nc * 6), torch.float32), ("cls_prob", (R, nc), torch.float32),
@@ -661,7 +693,9 @@ class Network(nn.Module):
             nb = int(np.prod(shape)) * torch.empty(0, dtype=dt).element_size()
             o = (o + 15) // 16 * 16
             out[name] = pack[o:o + nb].view(dt).view(*shape)
+            rec.append((name, o, o + nb, dt, shape))
             o += nb
+        Network._carve_layouts[(R, nc)] = (rec, o)
         return out, o
 
     def _static_stage(self, scene_t, dims, blobs=None, killing_inds=None, fused=None):
@@ -725,16 +759,20 @@ class Network(nn.Module):
 
         def __enter__(self):
             n, sl = self.net, self.slot
-            self.saved = (n._graphs, n._arena)
-            n._graphs, n._arena = sl["graphs"], sl["arena"]
+            d = n.__dict__  # plain attribute writes: nn.Module.__setattr__ costs ~5 us each
+            self.saved = (d["_graphs"], d["_arena"])
+            d["_graphs"], d["_arena"] = sl["graphs"], sl["arena"]
             self.ctx = torch.cuda.stream(sl["stream"]) if sl["stream"] is not None else None
             if self.ctx is not None:
                 self.ctx.__enter__()
+            self.old_pin = S.pin_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream))
 
         def __exit__(self, *exc):
+            S.pin_stream(self.old_pin)
             if self.ctx is not None:
                 self.ctx.__exit__(*exc)
-            self.net._graphs, self.net._arena = self.saved
+            d = self.net.__dict__
+            d["_graphs"], d["_arena"] = self.saved
 
     def _submit(self, blobs, killing_inds, slot):
         """Step 1 (async): input copies, static stage (graph replay), packed results -> pinned host (async D2H)."""
@@ -778,11 +816,15 @@ class Network(nn.Module):
                     torch.cuda.synchronize()
                     g = torch.cuda.CUDAGraph()
                     n0 = S.launch_count()
-                    with torch.cuda.graph(g):
-                        st["outs"] = self._static_stage(st["scene"], dims, blobs, None, fdev)
+                    pin = S.pin_stream(None)  # capture runs on torch's capture stream
+                    try:
+                        with torch.cuda.graph(g):
+                            st["outs"] = self._static_stage(st["scene"], dims, blobs, None, fdev)
+                    finally:
+                        S.pin_stream(pin)
                     st["graph"], st["n_kernels"] = g, S.launch_count() - n0
                 st["graph"].replay()
-                self._replayed_kernels += st["n_kernels"]
+                self.__dict__["_replayed_kernels"] += st["n_kernels"]
                 # results must not alias the replay buffers: ONE clone of the packed result buffer, then re-carve
                 pack = st["outs"]["pack"].clone()
                 outs, _ = self._carve(pack, int(cfg.TEST.RPN_POST_NMS_TOP_N), max(int(cfg.NUM_CLASSES), 1))
@@ -847,8 +889,7 @@ class Network(nn.Module):
         P = h["P"]
         if "bits_pin" in h:
             P["mask_bits_host"] = h["bits_pin"].numpy().copy()
-        self._scene_info, self._id, self._scene = h["scene_info"], h["id"], h["scene_t"]
-        self.batch_size, self._mode = 1, "TEST"
+        self.__dict__.update(_scene_info=h["scene_info"], _id=h["id"], _scene=h["scene_t"], batch_size=1, _mode="TEST")
         self._predictions.clear()
         self._predictions.update(h.get("debug", {}))
         self._predictions.update(P)
