@@ -18,7 +18,7 @@ extern "C" int64_t sis3d_launch_count(void) { return (int64_t)sis3d::g_launch_co
 // ---- host-side planner of the ragged mask stage (pure CPU code: the "runtime" part of the per-RoI mask head) ------
 // From the decoded detection table it lays out, in one byte blob that the caller ships with a single pinned H2D copy:
 // region tables of the first (windowed NCDHW scene -> canvas/compact) and last (-> dense per-crop output) layers, the
-// 8x2x8 brick list of the tensor-core layers (canvas mode) or the region table of the middle layers (compact mode), voxel
+// 4x4x8 brick list of the tensor-core layers (canvas mode) or the region table of the middle layers (compact mode), voxel
 // offsets, predicted classes, kept row indices and crop sizes.  Mirrors lib/nets/network.py:296-311 (crop selection).
 extern "C" int sis3d_mask_plan_build(const float *h_det, int n, int X, int Y, int Z, int ncls, int use_canvas, void *h_blob,
                                      size_t capacity, sis3d_mask_plan *plan) {
@@ -40,7 +40,7 @@ extern "C" int sis3d_mask_plan_build(const float *h_det, int n, int X, int Y, in
         xsum += w + 1;
         ymax = h > ymax ? h : ymax;
         zmax = l > zmax ? l : zmax;
-        ntiles += (int64_t)((w + 7) / 8) * ((h + 1) / 2) * ((l + 7) / 8);  // 8x2x8 bricks (csrc/conv_tc.cu)
+        ntiles += (int64_t)((w + 3) / 4) * ((h + 3) / 4) * ((l + 7) / 8);  // 4x4x8 bricks (sis3d_conv3d_tc_brick, tile-list mode)
         t_mid += ((int64_t)w * h * l + SIS3D_CONV_TILE_M - 1) / SIS3D_CONV_TILE_M;
     }
     p.total_voxels = total;
@@ -85,8 +85,8 @@ extern "C" int sis3d_mask_plan_build(const float *h_det, int n, int X, int Y, in
             f.out_stride[0] = cs0; f.out_stride[1] = cs1; f.out_stride[2] = cs2;
             q.in_off = xoff * cs0;
             q.in_stride[0] = cs0; q.in_stride[1] = cs1; q.in_stride[2] = cs2;
-            for (int bx = 0; bx < w; bx += 8)
-                for (int by = 0; by < h; by += 2)
+            for (int bx = 0; bx < w; bx += 4)
+                for (int by = 0; by < h; by += 4)
                     for (int bz = 0; bz < l; bz += 8) {
                         int32_t *t = tiles + tile_no * 8;
                         t[0] = (int32_t)xoff + bx; t[1] = by; t[2] = bz;

@@ -25,8 +25,8 @@
 
 namespace sis3d {
 
-constexpr int TC_BX = 8, TC_BY = 2, TC_BZ = 8;  // 128 voxels; rows ordered z (8 = one swizzle atom), y, x
-constexpr int TC_BM = TC_BX * TC_BY * TC_BZ;  // 128
+constexpr int TC_BZ = 8;  // brick = (16/BY) x BY x 8 voxels (x,y,z), BY in {2,4}; rows ordered z (8 = one swizzle atom), y, x
+constexpr int TC_BM = 128;
 constexpr int TC_KC = 32;                      // channels per stage: 32 * 4 B = 128 B = one swizzle row
 constexpr int TC_STAGES_MAX = 4;
 constexpr int TC_A_BYTES = TC_BM * 128;
@@ -125,18 +125,19 @@ struct TcStages { static constexpr int value = BN >= 128 ? 4 : 3; };
 // stage count per kernel flavour: the 3x3x3 stages are 3x bigger (slab + three weight tiles)
 template <int BN, int KS, int ROWB>
 struct TcStagesOf { static constexpr int value = KS == 3 ? 3 : TcStages<BN>::value; };
-template <int BN, int KS, int ROWB>
+template <int BN, int KS, int ROWB, int BY>
 constexpr size_t tc_smem_bytes() {
     return (size_t)TcStagesOf<BN, KS, ROWB>::value *
-               ((KS == 3 ? (TC_BX + 2) * TC_BY * TC_BZ : TC_BM) * ROWB + (KS == 3 ? 3 : 1) * BN * ROWB) + 1024 + 256;
+               ((KS == 3 ? (16 / BY + 2) * BY * TC_BZ : TC_BM) * ROWB + (KS == 3 ? 3 : 1) * BN * ROWB) + 1024 + 256;
 }
 
 // EB = operand element bytes: 4 -> fp32 storage, kind::tf32;  2 -> fp16 storage, kind::f16 (same 11-bit significand,
 // half the operand bytes through L2).  ROWB = bytes of one K slice row in shared memory (128, or 64 for C_in = 32 in fp16).
-template <int BN, int KS, int EB = 4, int ROWB = 128>
+template <int BN, int KS, int EB = 4, int ROWB = 128, int BY = 2>
 __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
     constexpr int KC = ROWB / EB;            // channels per pipeline stage
+    constexpr int TC_BY = BY, TC_BX = 16 / BY;  // brick: BY = 2 -> 8x2x8 (whole volumes), BY = 4 -> 4x4x8 (small RoI crops)
     // 3x3x3: one stage = one (dy, dz) pair: an x-halo slab of (8+2) x-planes (160 rows) serves the three x-taps --
     // tap dx reads rows [dx*16, dx*16+128), a whole-swizzle-atom offset -- plus the three taps' weight tiles.
     constexpr int XT = KS == 3 ? 3 : 1;      // x-taps per stage
@@ -343,17 +344,17 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-template <int BN, int KS, int EB = 4, int ROWB = 128>
+template <int BN, int KS, int EB = 4, int ROWB = 128, int BY = 2>
 static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcArgs &a, int n_tiles, cudaStream_t s) {
-    const size_t smem = tc_smem_bytes<BN, KS, ROWB>();
+    const size_t smem = tc_smem_bytes<BN, KS, ROWB, BY>();
     static bool attr_done = false;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(conv3d_k3_tc_kernel<BN, KS, EB, ROWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(conv3d_k3_tc_kernel<BN, KS, EB, ROWB, BY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return SIS3D_ELAUNCH;
         attr_done = true;
     }
     dim3 grid(n_tiles, a.cout / BN);
-    conv3d_k3_tc_kernel<BN, KS, EB, ROWB><<<grid, 128, smem, s>>>(tmA, tmB, a);
+    conv3d_k3_tc_kernel<BN, KS, EB, ROWB, BY><<<grid, 128, smem, s>>>(tmA, tmB, a);
     return finish_launch();
 }
 
@@ -402,6 +403,8 @@ extern "C" int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const floa
                                   int ks, const int32_t *tiles, int n_tiles, int act, void *stream) {
     if (!in || !w_tc || !out || X <= 0 || Y <= 0 || Z <= 0 || (ks != 1 && ks != 3)) return SIS3D_EINVAL;
     const int taps = ks * ks * ks;
+    // explicit tile lists (ragged RoI crops) use 4x4x8 bricks, whole volumes 8x2x8 (sis3d_conv3d_tc_brick)
+    const int by = (tiles && ks == 3 && cout == 64 && cin % 64 == 0) ? 4 : 2, bx = 16 / by;
     if (!sis3d_conv3d_k3_tc_supported(cin, cout)) return SIS3D_EUNSUPPORTED;
     if (((uintptr_t)in | (uintptr_t)w_tc | (uintptr_t)out) & 15) return SIS3D_EINVAL;
     if ((out_ld | out_coff | res_ld | res_coff) & 3) return SIS3D_EINVAL;
@@ -412,7 +415,7 @@ extern "C" int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const floa
     {
         cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X};
         cuuint64_t strides[3] = {(cuuint64_t)cin * 4, (cuuint64_t)Z * cin * 4, (cuuint64_t)Y * Z * cin * 4};
-        cuuint32_t box[4] = {TC_KC, TC_BZ, TC_BY, (cuuint32_t)(ks == 3 ? TC_BX + 2 : TC_BX)};
+        cuuint32_t box[4] = {TC_KC, TC_BZ, (cuuint32_t)by, (cuuint32_t)(ks == 3 ? bx + 2 : bx)};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -431,11 +434,12 @@ extern "C" int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const floa
     a.bias = bias; a.res = residual; a.out = out; a.tiles = tiles; a.out16 = nullptr;
     a.X = X; a.Y = Y; a.Z = Z; a.cin = cin; a.cout = cout; a.act = act;
     a.out_ld = out_ld; a.out_coff = out_coff; a.res_ld = res_ld; a.res_coff = res_coff;
-    a.tiles_y = cdiv(Y, TC_BY); a.tiles_z = cdiv(Z, TC_BZ);
-    if (!tiles) n_tiles = cdiv(X, TC_BX) * a.tiles_y * a.tiles_z;
+    a.tiles_y = cdiv(Y, by); a.tiles_z = cdiv(Z, TC_BZ);
+    if (!tiles) n_tiles = cdiv(X, bx) * a.tiles_y * a.tiles_z;
     if (n_tiles <= 0) return SIS3D_OK;
     cudaStream_t s = (cudaStream_t)stream;
     if (ks == 3) {
+        if (by == 4) return launch_tc<64, 3, 4, 128, 4>(tmA, tmB, a, n_tiles, s);
         switch (BN) {
             case 32: return launch_tc<32, 3>(tmA, tmB, a, n_tiles, s);
             case 64: return launch_tc<64, 3>(tmA, tmB, a, n_tiles, s);
@@ -538,12 +542,13 @@ extern "C" int sis3d_conv3d_tc_f16(const uint16_t *in16, const uint16_t *w16, co
     const int BN = wide ? (cout >= 128 ? 128 : cout) : (cout >= 64 ? 64 : cout);  // 64-B rows: N tiles of at most 64
     const int kc = wide ? 64 : 32;
     if (!wide && cin != 32) return SIS3D_EUNSUPPORTED;
+    const int by = (tiles && ks == 3 && cout == 64 && wide) ? 4 : 2, bx = 16 / by;
     const CUtensorMapSwizzle sw = wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUtensorMap tmA, tmB;
     {
         cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X};
         cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)Z * cin * 2, (cuuint64_t)Y * Z * cin * 2};
-        cuuint32_t box[4] = {(cuuint32_t)kc, TC_BZ, TC_BY, (cuuint32_t)(ks == 3 ? TC_BX + 2 : TC_BX)};
+        cuuint32_t box[4] = {(cuuint32_t)kc, TC_BZ, (cuuint32_t)by, (cuuint32_t)(ks == 3 ? bx + 2 : bx)};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void *)in16, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -562,11 +567,12 @@ extern "C" int sis3d_conv3d_tc_f16(const uint16_t *in16, const uint16_t *w16, co
     a.bias = bias; a.res = residual; a.out = out32; a.out16 = (__half *)out16; a.tiles = tiles;
     a.X = X; a.Y = Y; a.Z = Z; a.cin = cin; a.cout = cout; a.act = act;
     a.out_ld = out_ld; a.out_coff = out_coff; a.res_ld = res_ld; a.res_coff = res_coff;
-    a.tiles_y = cdiv(Y, TC_BY); a.tiles_z = cdiv(Z, TC_BZ);
-    if (!tiles) n_tiles = cdiv(X, TC_BX) * a.tiles_y * a.tiles_z;
+    a.tiles_y = cdiv(Y, by); a.tiles_z = cdiv(Z, TC_BZ);
+    if (!tiles) n_tiles = cdiv(X, bx) * a.tiles_y * a.tiles_z;
     if (n_tiles <= 0) return SIS3D_OK;
     cudaStream_t s = (cudaStream_t)stream;
     if (wide) {
+        if (ks == 3 && by == 4) return launch_tc<64, 3, 2, 128, 4>(tmA, tmB, a, n_tiles, s);
         if (ks == 3) {
             switch (BN) {
                 case 32: return launch_tc<32, 3, 2, 128>(tmA, tmB, a, n_tiles, s);
@@ -582,4 +588,12 @@ extern "C" int sis3d_conv3d_tc_f16(const uint16_t *in16, const uint16_t *w16, co
     }
     if (ks == 3) return BN == 32 ? launch_tc<32, 3, 2, 64>(tmA, tmB, a, n_tiles, s) : launch_tc<64, 3, 2, 64>(tmA, tmB, a, n_tiles, s);
     return BN == 32 ? launch_tc<32, 1, 2, 64>(tmA, tmB, a, n_tiles, s) : launch_tc<64, 1, 2, 64>(tmA, tmB, a, n_tiles, s);
+}
+
+// brick shape the tensor-core kernel uses for a layer (so callers can build matching tile lists)
+extern "C" void sis3d_conv3d_tc_brick(int with_tile_list, int ks, int cin, int cout, int32_t *bx, int32_t *by, int32_t *bz) {
+    const int y = (with_tile_list && ks == 3 && cout == 64 && cin % 64 == 0) ? 4 : 2;
+    if (bx) *bx = 16 / y;
+    if (by) *by = y;
+    if (bz) *bz = TC_BZ;
 }

@@ -582,7 +582,7 @@ class Network(nn.Module):
         one zeroed canvas [sum(w_j + 1), max h, max l, 64] (one zero slab between crops = the crop-border
         zero padding), so each of the six layers is ONE launch: layer 1 (C_in = 2, windowed NCDHW scene) and
         the 1x1 head on the fp32 CUDA-core kernel, the four 64->64 3x3x3 layers on the tcgen05 kernel driven
-        by an explicit list of 8x2x8 bricks.  The tables come from the native planner (sis3d_mask_plan_build)
+        by an explicit list of 4x4x8 bricks.  The tables come from the native planner (sis3d_mask_plan_build)
         and travel in ONE pinned H2D copy; all buffers come from a grow-only arena."""
         dev = scene_ncdhw.device
         X, Y, Z = (int(v) for v in scene_ncdhw.shape[2:])

@@ -159,12 +159,14 @@ int sis3d_mlp_tail(const float *x1, int R, int d1, const float *w2, const float 
  * tcgen05.mma kind::tf32 with fp32 accumulation in TMEM, operands staged by 4-D/2-D TMA boxes
  * (csrc/conv_tc.cu).  `in` is a dense VC tensor [X][Y][Z][cin]; w_tc comes from
  * sis3d_pack_conv_weight_tc ([cout][ks^3*cin]).  tiles == NULL covers the whole volume with 8x2x8 (x,y,z)
- * bricks; otherwise tiles int32[n_tiles][8] = {x0,y0,z0,x1,y1,z1,0,0} lists brick origins and the
+ * bricks; otherwise (brick shape from sis3d_conv3d_tc_brick) tiles int32[n_tiles][8] = {x0,y0,z0,x1,y1,z1,0,0} lists brick origins and the
  * exclusive end of the voxels to be written (ragged RoI crops packed on one canvas).
  * Requires cin % 32 == 0 and cout in {32, 64, 128k}; returns SIS3D_EUNSUPPORTED otherwise.
  * ---------------------------------------------------------------------------------------------- */
 int sis3d_pack_conv_weight_tc(const float *w_oidhw, int cout, int cin, int ks, float *w_tc, void *stream);
 int sis3d_conv3d_k3_tc_supported(int cin, int cout);
+/* brick shape (x,y,z) the kernel uses for a layer: 8x2x8 for whole volumes, 4x4x8 for explicit tile lists of 64->64 layers */
+void sis3d_conv3d_tc_brick(int with_tile_list, int ks, int cin, int cout, int32_t *bx, int32_t *by, int32_t *bz);
 int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const float *bias, const float *residual,
                        int res_ld, int res_coff, float *out, int out_ld, int out_coff, int X, int Y,
                        int Z, int cin, int cout, int ks, const int32_t *tiles, int n_tiles, int act, void *stream);

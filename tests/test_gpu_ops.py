@@ -401,9 +401,11 @@ def test_conv3d_tc_tile_list(S):
     w = (rng.standard_normal((cout, cin, 3, 3, 3)) / np.sqrt(cin * 27)).astype(np.float32)
     tiles = []
     for (x0, c), s in zip(crops, sizes):
-        for bx in range(0, s[0], 8):  # 8x2x8 bricks (csrc/conv_tc.cu)
-            for by in range(0, s[1], 2):
-                for bz in range(0, s[2], 8):
+        bx_, by_, bz_ = C.c_int32(), C.c_int32(), C.c_int32()
+        S.lib.sis3d_conv3d_tc_brick(1, 3, cin, cout, C.byref(bx_), C.byref(by_), C.byref(bz_))
+        for bx in range(0, s[0], bx_.value):
+            for by in range(0, s[1], by_.value):
+                for bz in range(0, s[2], bz_.value):
                     tiles.append([x0 + bx, by, bz, x0 + s[0], s[1], s[2], 0, 0])
     td = torch.tensor(tiles, dtype=torch.int32, device=DEV)
     wtc = torch.empty(cout, 27 * cin, device=DEV)
