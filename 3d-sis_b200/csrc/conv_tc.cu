@@ -124,7 +124,7 @@ template <int BN>
 struct TcStages { static constexpr int value = BN >= 128 ? 4 : 3; };
 // stage count per kernel flavour: the 3x3x3 stages are 3x bigger (slab + three weight tiles)
 template <int BN, int KS, int ROWB>
-struct TcStagesOf { static constexpr int value = KS == 3 ? 3 : TcStages<BN>::value; };
+struct TcStagesOf { static constexpr int value = KS == 3 ? (BN >= 128 ? 3 : 2) : TcStages<BN>::value; };  // narrow 3x3x3 layers: 2 stages so 2-3 CTAs share an SM
 template <int BN, int KS, int ROWB, int BY>
 constexpr size_t tc_smem_bytes() {
     return (size_t)TcStagesOf<BN, KS, ROWB>::value *
