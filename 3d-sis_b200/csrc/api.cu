@@ -1,4 +1,5 @@
 // api.cu -- library-wide entry points of libsis3d.so.
+#include <math.h>
 #include "common.cuh"
 namespace sis3d { unsigned long long g_launch_count = 0; }
 
@@ -114,5 +115,58 @@ extern "C" int sis3d_mask_plan_build(const float *h_det, int n, int X, int Y, in
     offs[nk] = voff;
     p.tiles_first = p.tiles_last = p.tiles_mid = tb;
     *plan = p;
+    return SIS3D_OK;
+}
+
+// ---- per-view constants of the back-projection, host code (lib/layer_utils/projection.py:27-60) ---------------------------
+// Packs world_to_camera | grid_to_world | clamped frustum AABB for every view into out[n][40] (layout of sis3d_project_map).
+// The two 4x4 inverses are supplied by the caller (torch.inverse, as in the reference); the 8-corner frustum bounds are
+// computed here with the arithmetic of the reference's tiny torch.bmm calls (fp32, separate multiply and add, k = 0..3)
+// so the cull bounds are bit-identical (checked on random poses in tests/test_view_params.py).
+static inline void matvec4(const float *m, const float *v, float *o) {
+    for (int r = 0; r < 4; ++r) {
+        volatile float acc = 0.f;  // volatile: one rounding per multiply and per add, never an FMA
+        for (int k = 0; k < 4; ++k) {
+            volatile float p = m[r * 4 + k] * v[k];
+            acc = acc + p;
+        }
+        o[r] = acc;
+    }
+}
+extern "C" int sis3d_view_params_host(const float *poses, const float *w2g, const float *inv_poses, const float *inv_w2g, int n,
+                                      int n_w2g, double fx, double fy, double cx, double cy, int img_w, int img_h,
+                                      double depth_min, double depth_max, int X, int Y, int Z, float *out) {
+    if (!poses || !w2g || !inv_poses || !inv_w2g || !out || n <= 0 || (n_w2g != 1 && n_w2g != n)) return SIS3D_EINVAL;
+    float corners[8][4];
+    int c = 0;
+    const double ds[2] = {depth_min, depth_max};
+    for (int di = 0; di < 2; ++di) {
+        const int ux[4] = {0, img_w - 1, img_w - 1, 0}, uy[4] = {0, 0, img_h - 1, img_h - 1};
+        for (int j = 0; j < 4; ++j, ++c) {  // depth_to_skeleton in Python doubles, stored as fp32 (projection.py:16-19)
+            const double x = (ux[j] - cx) / fx, y = (uy[j] - cy) / fy;
+            corners[c][0] = (float)(ds[di] * x); corners[c][1] = (float)(ds[di] * y); corners[c][2] = (float)ds[di]; corners[c][3] = 1.f;
+        }
+    }
+    const float dims[3] = {(float)X, (float)Y, (float)Z};
+    for (int i = 0; i < n; ++i) {
+        const float *c2w = poses + 16 * i, *g = w2g + 16 * (n_w2g == 1 ? 0 : i);
+        float *o = out + 40 * i;
+        for (int k = 0; k < 16; ++k) { o[k] = inv_poses[16 * i + k]; o[16 + k] = inv_w2g[16 * (n_w2g == 1 ? 0 : i) + k]; }
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int k = 0; k < 8; ++k) {
+            float p[4], pf[4], pc[4], l[4], u[4];
+            matvec4(c2w, corners[k], p);
+            for (int r = 0; r < 4; ++r) { pf[r] = floorf(p[r]); pc[r] = ceilf(p[r]); }
+            matvec4(g, pf, l);
+            matvec4(g, pc, u);
+            for (int r = 0; r < 3; ++r) {
+                const float a = nearbyintf(l[r]), b = nearbyintf(u[r]);  // torch.round: half to even
+                lo[r] = fminf(lo[r], fminf(a, b));
+                hi[r] = fmaxf(hi[r], fmaxf(a, b));
+            }
+        }
+        for (int r = 0; r < 3; ++r) { o[32 + r] = fmaxf(lo[r], 0.f); o[35 + r] = fminf(hi[r], dims[r]); }
+        o[38] = o[39] = 0.f;
+    }
     return SIS3D_OK;
 }

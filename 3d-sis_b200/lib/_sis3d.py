@@ -52,7 +52,7 @@ TILE_M = 64
 
 # every exported symbol of include/sis3d.h (checked by tests/test_abi.py)
 SYMBOLS = ["sis3d_strerror", "sis3d_version", "sis3d_launch_count", "sis3d_nms_workspace_bytes", "sis3d_nms",
-           "sis3d_roi_pool_fwd", "sis3d_roi_pool_levels", "sis3d_project_map", "sis3d_project_compact",
+           "sis3d_roi_pool_fwd", "sis3d_roi_pool_levels", "sis3d_view_params_host", "sis3d_project_map", "sis3d_project_compact",
            "sis3d_project_compact_workspace_bytes", "sis3d_backproject_pairs", "sis3d_project_scatter_lists",
            "sis3d_backproject_max", "sis3d_backproject_conv_k2s2_workspace_bytes", "sis3d_backproject_conv_k2s2",
            "sis3d_pack_conv_weight", "sis3d_conv3d", "sis3d_maxpool3",

@@ -48,16 +48,32 @@ def view_params(intrinsic, image_dims, depth_min, depth_max, volume_dims, depths
 
 
 def _view_params_impl(intrinsic, image_dims, depth_min, depth_max, volume_dims, poses, world2grid):
+    poses = torch.as_tensor(poses, dtype=torch.float32).reshape(-1, 4, 4).cpu().contiguous()
+    n = poses.shape[0]
+    w2g = torch.as_tensor(world2grid, dtype=torch.float32).cpu().reshape(-1, 4, 4).contiguous()
+    if w2g.shape[0] not in (1, n):
+        raise S.Sis3dError("world2grid must be one matrix or one per view")
+    # the reference's own inverses (projection.py:56-57); LAPACK handles each 4x4 of the batch independently
+    inv = torch.inverse(torch.cat((poses, w2g))).contiguous()
+    inv_p, inv_g = inv[:n], inv[n:]
+    out = torch.empty(n, 40, dtype=torch.float32)
+    S.check(S.lib.sis3d_view_params_host(C.c_void_p(poses.data_ptr()), C.c_void_p(w2g.data_ptr()), C.c_void_p(inv_p.data_ptr()),
+                                         C.c_void_p(inv_g.data_ptr()), n, w2g.shape[0], C.c_double(intrinsic[0][0]),
+                                         C.c_double(intrinsic[1][1]), C.c_double(intrinsic[0][2]), C.c_double(intrinsic[1][2]),
+                                         int(image_dims[0]), int(image_dims[1]), C.c_double(depth_min), C.c_double(depth_max),
+                                         int(volume_dims[0]), int(volume_dims[1]), int(volume_dims[2]),
+                                         C.c_void_p(out.data_ptr())), "view_params_host")
+    return out
+
+
+def _view_params_torch(intrinsic, image_dims, depth_min, depth_max, volume_dims, poses, world2grid):
+    """The same computation with the reference's torch ops (kept as the in-repo cross-check of the native helper)."""
     poses = torch.as_tensor(poses, dtype=torch.float32).reshape(-1, 4, 4).cpu()
     n = poses.shape[0]
     w2g = torch.as_tensor(world2grid, dtype=torch.float32).cpu().reshape(-1, 4, 4)
     if w2g.shape[0] == 1:
         w2g = w2g.expand(n, 4, 4).contiguous()
-    key = (float(intrinsic[0][0]), float(intrinsic[1][1]), float(intrinsic[0][2]), float(intrinsic[1][2]),
-           int(image_dims[0]), int(image_dims[1]), float(depth_min), float(depth_max))
-    corners = _CORNER_CACHE.get(key)
-    if corners is None:
-        corners = _CORNER_CACHE[key] = _corner_rays(intrinsic, image_dims, depth_min, depth_max)
+    corners = _corner_rays(intrinsic, image_dims, depth_min, depth_max)
     out = torch.zeros(n, 40, dtype=torch.float32)
     out[:, 0:16] = torch.inverse(poses).reshape(n, 16)
     out[:, 16:32] = torch.inverse(w2g).reshape(n, 16)

@@ -825,10 +825,21 @@ class Network(nn.Module):
                     st["graph"], st["n_kernels"] = g, S.launch_count() - n0
                 st["graph"].replay()
                 self.__dict__["_replayed_kernels"] += st["n_kernels"]
-                # results must not alias the replay buffers: ONE clone of the packed result buffer, then re-carve
-                pack = st["outs"]["pack"].clone()
-                outs, _ = self._carve(pack, int(cfg.TEST.RPN_POST_NMS_TOP_N), max(int(cfg.NUM_CLASSES), 1))
-                outs["num"] = outs["num"][:1]
+                # results must not alias the replay buffers: ONE copy of the packed result buffer into one of two
+                # slot-owned, pre-carved result buffers (valid until this slot has been reused twice)
+                ring = st.get("result_ring")
+                if ring is None:
+                    ring = st["result_ring"] = []
+                    for _ in range(2):
+                        pk = torch.empty_like(st["outs"]["pack"])
+                        o, _ = self._carve(pk, int(cfg.TEST.RPN_POST_NMS_TOP_N), max(int(cfg.NUM_CLASSES), 1))
+                        o["num"] = o["num"][:1]
+                        o["pack"] = pk
+                        ring.append(o)
+                    st["ring_pos"] = 0
+                outs = ring[st["ring_pos"]]
+                st["ring_pos"] ^= 1
+                outs["pack"].copy_(st["outs"]["pack"], non_blocking=True)
                 scene_t = st["scene"]
             else:
                 scene_t = data.to(dev, torch.float32, non_blocking=True).contiguous()

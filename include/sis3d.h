@@ -77,6 +77,11 @@ int sis3d_roi_pool_levels(const float *feat1, const float *feat2, const float *f
  *                         (reference layout) are first transposed to [n_views][h*w][C] into
  *                         `feats_t` (workspace of the same size).
  * ---------------------------------------------------------------------------------------------- */
+/* Host helper (CPU code): packs the per-view constants views[n][40] from the poses, world2grid and their inverses
+ * (the caller inverts the 4x4s, e.g. torch.inverse as the reference does); frustum bounds per projection.py:27-60. */
+int sis3d_view_params_host(const float *h_poses, const float *h_w2g, const float *h_inv_poses, const float *h_inv_w2g,
+                           int n, int n_w2g, double fx, double fy, double cx, double cy, int img_w, int img_h,
+                           double depth_min, double depth_max, int X, int Y, int Z, float *h_out);
 int sis3d_project_map(const float *views, const float *depth, int n_views, int img_w, int img_h,
                       float fx, float fy, float cx, float cy, float depth_min, float depth_max, float voxel_size,
                       int X, int Y, int Z, int16_t *pix, int32_t *counts, void *stream);
