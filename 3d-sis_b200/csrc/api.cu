@@ -118,6 +118,89 @@ extern "C" int sis3d_mask_plan_build(const float *h_det, int n, int X, int Y, in
     return SIS3D_OK;
 }
 
+// ---- ragged mask stage: every launch of one scene's mask head behind ONE host call ---------------------------------------
+// (reference: lib/nets/network.py:283-317 loops over the kept RoIs and runs mask_backbone on each crop).  The tables come
+// from sis3d_mask_plan_build (pinned host blob); this call queues their H2D copy, zeroes the canvases, launches the six
+// layers + the predicted-class select and, when bits_host is given, the D2H copy of the thresholded masks.
+extern "C" int sis3d_mask_stage_launch(const sis3d_mask_plan *p, const void *h_blob, const sis3d_mask_stage *a, void *stream) {
+    if (!p || !h_blob || !a || !a->scene || !a->w_first || !a->w_last || !a->tables || !a->canvas || !a->masks) return SIS3D_EINVAL;
+    const int nk = p->n_kept, ncls = a->ncls;
+    if (nk <= 0) return SIS3D_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t total = p->total_voxels;
+    const int Xc = p->canvas[0], Yc = p->canvas[1], Zc = p->canvas[2];
+    const int64_t cvox = (int64_t)Xc * Yc * Zc;
+    const size_t need = a->math == 0 ? (size_t)total * 64 * 4 * 2 : (size_t)cvox * 64 * (a->math == 2 ? 2 : 4) * 2;
+    if (a->canvas_bytes < need) return SIS3D_EWORKSPACE;
+    if (a->math == 2 && (!a->canvas32 || a->canvas32_bytes < (size_t)cvox * 64 * 4)) return SIS3D_EWORKSPACE;
+    for (int i = 0; i < 4; ++i)
+        if (!a->w_mid[i]) return SIS3D_EINVAL;
+    if (cudaMemcpyAsync(a->tables, h_blob, (size_t)p->bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return SIS3D_ELAUNCH;
+    char *tb = (char *)a->tables;
+    const sis3d_region *r_first = (const sis3d_region *)(tb + p->off_first), *r_last = (const sis3d_region *)(tb + p->off_last);
+    const int64_t scene_vox = (int64_t)a->X * a->Y * a->Z;
+    int rc;
+    const float *x32 = nullptr;
+    if (a->math == 0) {  // compact per-crop buffers, fp32 CUDA-core kernel throughout
+        float *b0 = (float *)a->canvas, *b1 = b0 + total * 64;
+        const sis3d_region *r_mid = (const sis3d_region *)(tb + p->off_rest);
+        if ((rc = sis3d_conv3d_ex(a->scene, scene_vox, a->w_first, nullptr, nullptr, 0, 0, b0, nullptr, 64, 0, r_first, nk,
+                                  p->tiles_first, 2, 64, 3, 1, 1, 1, stream))) return rc;
+        float *cur = b0, *nxt = b1;
+        for (int i = 0; i < 4; ++i) {
+            if ((rc = sis3d_conv3d_ex(cur, 1, (const float *)a->w_mid[i], nullptr, nullptr, 0, 0, nxt, nullptr, 64, 0, r_mid, nk,
+                                      p->tiles_mid, 64, 64, 3, 1, 1, 1, stream))) return rc;
+            float *t = cur; cur = nxt; nxt = t;
+        }
+        x32 = cur;
+    } else {
+        const int32_t *tiles = (const int32_t *)(tb + p->off_rest);
+        if (cudaMemsetAsync(a->canvas, 0, need, st) != cudaSuccess) return SIS3D_ELAUNCH;
+        if (a->math == 2) {
+            uint16_t *h0 = (uint16_t *)a->canvas, *h1 = h0 + cvox * 64;
+            if ((rc = sis3d_conv3d_ex(a->scene, scene_vox, a->w_first, nullptr, nullptr, 0, 0, nullptr, h0, 64, 0, r_first, nk,
+                                      p->tiles_first, 2, 64, 3, 1, 1, 1, stream))) return rc;
+            uint16_t *cur = h0, *nxt = h1;
+            for (int i = 0; i < 4; ++i) {
+                const bool last3 = i == 3;
+                if ((rc = sis3d_conv3d_tc_f16(cur, (const uint16_t *)a->w_mid[i], nullptr, nullptr, 0, 0, last3 ? a->canvas32 : nullptr,
+                                              last3 ? nullptr : nxt, 64, 0, Xc, Yc, Zc, 64, 64, 3, tiles, p->n_tiles_tc, 1, stream)))
+                    return rc;
+                uint16_t *t = cur; cur = nxt; nxt = t;
+            }
+            x32 = a->canvas32;
+        } else {
+            float *b0 = (float *)a->canvas, *b1 = b0 + cvox * 64;
+            if ((rc = sis3d_conv3d_ex(a->scene, scene_vox, a->w_first, nullptr, nullptr, 0, 0, b0, nullptr, 64, 0, r_first, nk,
+                                      p->tiles_first, 2, 64, 3, 1, 1, 1, stream))) return rc;
+            float *cur = b0, *nxt = b1;
+            for (int i = 0; i < 4; ++i) {
+                if ((rc = sis3d_conv3d_k3_tc(cur, (const float *)a->w_mid[i], nullptr, nullptr, 0, 0, nxt, 64, 0, Xc, Yc, Zc, 64, 64,
+                                             3, tiles, p->n_tiles_tc, 1, stream))) return rc;
+                float *t = cur; cur = nxt; nxt = t;
+            }
+            x32 = cur;
+        }
+    }
+    if ((rc = sis3d_conv3d_ex(x32, 1, a->w_last, nullptr, nullptr, 0, 0, a->masks, nullptr, ncls, 0, r_last, nk, p->tiles_last, 64,
+                              ncls, 1, 1, 0, 2, stream))) return rc;
+    if (a->bits) {
+        if ((rc = sis3d_mask_select(a->masks, (const int64_t *)(tb + p->off_offs), (const int32_t *)(tb + p->off_cls), nk, ncls,
+                                    total, a->thresh, nullptr, a->bits, stream))) return rc;
+        if (a->bits_host && cudaMemcpyAsync(a->bits_host, a->bits, (size_t)total, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+            return SIS3D_ELAUNCH;
+    }
+    return SIS3D_OK;
+}
+
+// thin async-copy entry point for hosts that stage their own pinned buffers (kind: 1 H2D, 2 D2H, 3 D2D)
+extern "C" int sis3d_memcpy_async(void *dst, const void *src, size_t bytes, int kind, void *stream) {
+    if (!dst || !src) return SIS3D_EINVAL;
+    if (bytes == 0) return SIS3D_OK;
+    const cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    return cudaMemcpyAsync(dst, src, bytes, k, (cudaStream_t)stream) == cudaSuccess ? SIS3D_OK : SIS3D_ELAUNCH;
+}
+
 // ---- per-view constants of the back-projection, host code (lib/layer_utils/projection.py:27-60) ---------------------------
 // Packs world_to_camera | grid_to_world | clamped frustum AABB for every view into out[n][40] (layout of sis3d_project_map).
 // The two 4x4 inverses are supplied by the caller (torch.inverse, as in the reference); the 8-corner frustum bounds are

@@ -47,6 +47,15 @@ class MaskPlan(C.Structure):
                 ("off_kept", C.c_int64), ("off_sizes", C.c_int64), ("bytes", C.c_int64)]
 
 
+class MaskStage(C.Structure):
+    """struct sis3d_mask_stage (include/sis3d.h)."""
+    _fields_ = [("scene", C.c_void_p), ("X", C.c_int32), ("Y", C.c_int32), ("Z", C.c_int32), ("ncls", C.c_int32),
+                ("math", C.c_int32), ("reserved", C.c_int32), ("w_first", C.c_void_p), ("w_last", C.c_void_p),
+                ("w_mid", C.c_void_p * 4), ("tables", C.c_void_p), ("canvas", C.c_void_p), ("canvas_bytes", C.c_size_t),
+                ("canvas32", C.c_void_p), ("canvas32_bytes", C.c_size_t), ("masks", C.c_void_p), ("bits", C.c_void_p),
+                ("bits_host", C.c_void_p), ("thresh", C.c_float), ("reserved2", C.c_int32)]
+
+
 REGION_BYTES = C.sizeof(Region)
 TILE_M = 64
 
@@ -58,7 +67,8 @@ SYMBOLS = ["sis3d_strerror", "sis3d_version", "sis3d_launch_count", "sis3d_nms_w
            "sis3d_pack_conv_weight", "sis3d_conv3d", "sis3d_maxpool3",
            "sis3d_vc_to_ncdhw", "sis3d_pack_conv_weight_tc_f16", "sis3d_cast_f16", "sis3d_conv3d_tc_f16", "sis3d_conv3d_ex",
            "sis3d_backproject_conv_k2s2_ex", "sis3d_linear_workspace_bytes", "sis3d_linear", "sis3d_linear_tc_supported", "sis3d_linear_tc_workspace_bytes", "sis3d_linear_tc", "sis3d_mlp_tail", "sis3d_pack_conv_weight_tc", "sis3d_conv3d_k3_tc_supported", "sis3d_conv3d_tc_brick", "sis3d_conv3d_k3_tc",
-           "sis3d_rpn_workspace_bytes", "sis3d_rpn_proposals", "sis3d_detect_decode", "sis3d_mask_plan_build", "sis3d_mask_select"]
+           "sis3d_rpn_workspace_bytes", "sis3d_rpn_proposals", "sis3d_detect_decode", "sis3d_mask_plan_build", "sis3d_mask_stage_launch", "sis3d_memcpy_async",
+           "sis3d_mask_select"]
 
 lib.sis3d_strerror.restype = C.c_char_p
 lib.sis3d_launch_count.restype = C.c_int64

@@ -98,7 +98,9 @@ class Network(nn.Module):
         self._packed_h = {}
         # conv math: 'tf32' = tcgen05 with fp32-stored operands (default), 'fp16' = tcgen05 with fp16-stored operands
         # (same 11-bit significand, half the L2 traffic), 'fp32' = CUDA-core exact path
-        self._math = os.environ.get("SIS3D_CONV_MATH", str(cfg.get("CONV_MATH", "tf32"))).lower()
+        # 'mixed' = TF32 operands in the static stage, fp16-stored operands in the ragged mask stage, which is bound by
+        # the L2->SM operand feed (profiles/): halving the operand bytes there is worth more than anywhere else
+        self.set_conv_math(os.environ.get("SIS3D_CONV_MATH", str(cfg.get("CONV_MATH", "tf32"))).lower())
         self._graphs = {}
         self._slots = []
         self._branches = os.environ.get("SIS3D_BRANCHES", "1") != "0"
@@ -176,6 +178,13 @@ class Network(nn.Module):
 
     def _version(self):
         return tuple((n, p._version, p.data_ptr()) for n, p in self.named_parameters())
+
+    def set_conv_math(self, mode):
+        """'fp32' CUDA-core exact path | 'tf32' | 'fp16' | 'mixed' (TF32 static stage + fp16-operand mask stage)."""
+        if mode not in ("fp32", "tf32", "fp16", "mixed"):
+            raise S.Sis3dError(f"unknown conv math {mode!r} (fp32 | tf32 | fp16 | mixed)")
+        self.__dict__["_math"] = "tf32" if mode == "mixed" else mode
+        self.__dict__["_mask_math"] = "fp16" if mode == "mixed" else mode
 
     def _ensure_packed(self):
         if not torch.cuda.is_available():
@@ -604,77 +613,37 @@ class Network(nn.Module):
         if nk == 0:
             return []
         nbytes, total = int(plan.bytes), int(plan.total_voxels)
-        tables = self._ws("mask_tables", nbytes, torch.uint8, dev)
-        tables.copy_(stage[:nbytes], non_blocking=True)
         host = stage.numpy()
         offs = host[plan.off_offs:plan.off_offs + 8 * (nk + 1)].view(np.int64).copy()
         sizes = host[plan.off_sizes:plan.off_sizes + 12 * nk].view(np.int32).reshape(nk, 3).copy()
-        rb = nk * S.REGION_BYTES
-        r_first, r_last = tables[plan.off_first:plan.off_first + rb], tables[plan.off_last:plan.off_last + rb]
-        d_offs = tables[plan.off_offs:plan.off_offs + 8 * (nk + 1)]
-        d_cls = tables[plan.off_cls:plan.off_cls + 4 * nk]
-        t_first, t_last = int(plan.tiles_first), int(plan.tiles_last)
-        outb = torch.empty(total * ncls, dtype=torch.float32, device=dev)  # handed to the caller (mask_pred views)
-        scene = Act(scene_ncdhw, (X, Y, Z), 2, layout="ncdhw")
-        if use_tc:
-            Xc, Yc, Zc = (int(v) for v in plan.canvas)
-            n_tiles = int(plan.n_tiles_tc)
-            r_tiles = tables[plan.off_rest:plan.off_rest + 32 * n_tiles]
-            cvox = Xc * Yc * Zc
-            if self._math == "fp16" and "mask_backbone.geometry.2" in self._packed_h:
-                # fp16 canvases between the layers (zeroed: the slabs between crops are the zero padding); the last
-                # 3x3x3 layer writes fp32 for the 1x1 head, which reads crop voxels only (no zeroing needed)
-                c16 = self._ws("mask_canvas16", 2 * cvox * 64, torch.float16, dev)
-                c16.zero_()
-                h = [c16[:cvox * 64], c16[cvox * 64:]]
-                c32 = self._ws("mask_canvas32", cvox * 64, torch.float32, dev)
-                self._conv(scene, "mask_backbone.geometry.0", act=1, regions=(r_first, t_first), out_dims=(Xc, Yc, Zc),
-                           out=Act(None, (Xc, Yc, Zc), 64), out16=h[0])
-                cur = 0
-                for idx in (2, 4, 6, 8):
-                    name = f"mask_backbone.geometry.{idx}"
-                    last3 = idx == 8
-                    tok = self._rec(f"conv_tc16[{name}]")
-                    S.check(S.lib.sis3d_conv3d_tc_f16(S.ptr(h[cur]), S.ptr(self._packed_h[name]), None, None, 0, 0,
-                                                      S.ptr(c32) if last3 else None, None if last3 else S.ptr(h[1 - cur]), 64, 0,
-                                                      Xc, Yc, Zc, 64, 64, 3, S.ptr(r_tiles), n_tiles, 1, S.stream()),
-                            f"conv3d_tc_f16[{name}]")
-                    self._rec_end(tok)
-                    cur = 1 - cur
-                x = Act(c32, (Xc, Yc, Zc), 64)
-            else:
-                canv = self._ws("mask_canvas", 2 * cvox * 64, torch.float32, dev)
-                canv.zero_()
-                bufs = [canv[:cvox * 64], canv[cvox * 64:]]
-                x = self._conv(scene, "mask_backbone.geometry.0", act=1, regions=(r_first, t_first), out_dims=(Xc, Yc, Zc),
-                               out=Act(bufs[0], (Xc, Yc, Zc), 64))
-                for li, idx in enumerate((2, 4, 6, 8)):
-                    name = f"mask_backbone.geometry.{idx}"
-                    dst = Act(bufs[(li + 1) % 2], (Xc, Yc, Zc), 64)
-                    tok = self._rec(f"conv_tc[{name}]")
-                    S.check(S.lib.sis3d_conv3d_k3_tc(S.ptr(x.t), S.ptr(self._packed_tc[name]), None, None, 0, 0, S.ptr(dst.t), 64,
-                                                     0, Xc, Yc, Zc, 64, 64, 3, S.ptr(r_tiles), n_tiles, 1, S.stream()),
-                            f"conv3d_k3_tc[{name}]")
-                    self._rec_end(tok)
-                    x = dst
-        else:
-            r_mid, t_mid = tables[plan.off_rest:plan.off_rest + rb], int(plan.tiles_mid)
-            act_buf = self._ws("mask_act", 2 * total * 64, torch.float32, dev)
-            bufs = [act_buf[:total * 64], act_buf[total * 64:]]
-            x = self._conv(scene, "mask_backbone.geometry.0", act=1, regions=(r_first, t_first), out_dims=(total, 1, 1),
-                           out=Act(bufs[0], (total, 1, 1), 64))
-            for li, idx in enumerate((2, 4, 6, 8)):
-                x = self._conv(x, f"mask_backbone.geometry.{idx}", act=1, regions=(r_mid, t_mid), out_dims=(total, 1, 1),
-                               out=Act(bufs[(li + 1) % 2], (total, 1, 1), 64))
-        y = self._conv(x, "mask_backbone.geometry.10", pad=0, act=2, regions=(r_last, t_last), out_dims=(total, 1, 1),
-                       out=Act(outb, (total, 1, 1), ncls))
-        # predicted-class channel of every kept RoI, thresholded, packed: ONE small D2H for the driver
+        math = 0 if not use_tc else (2 if (self._mask_math == "fp16" and "mask_backbone.geometry.2" in self._packed_h) else 1)
+        cvox = int(plan.canvas[0]) * int(plan.canvas[1]) * int(plan.canvas[2])
+        a = S.MaskStage()
+        a.scene, a.X, a.Y, a.Z, a.ncls, a.math = scene_ncdhw.data_ptr(), X, Y, Z, ncls, math
+        a.w_first = self._packed["mask_backbone.geometry.0"][0].data_ptr()
+        a.w_last = self._packed["mask_backbone.geometry.10"][0].data_ptr()
+        table = (self._packed, self._packed_tc, self._packed_h)[math]
+        for i, idx in enumerate((2, 4, 6, 8)):
+            w = table[f"mask_backbone.geometry.{idx}"]
+            a.w_mid[i] = (w[0] if math == 0 else w).data_ptr()
+        a.tables = self._ws("mask_tables", nbytes, torch.uint8, dev).data_ptr()
+        a.canvas_bytes = 2 * 64 * (total * 4 if math == 0 else cvox * (2 if math == 2 else 4))
+        a.canvas = self._ws("mask_canvas", a.canvas_bytes, torch.uint8, dev).data_ptr()
+        if math == 2:
+            a.canvas32_bytes = cvox * 64 * 4
+            a.canvas32 = self._ws("mask_canvas32", a.canvas32_bytes, torch.uint8, dev).data_ptr()
+        # handed to the caller (mask_pred views / packed bits): fresh allocations, not arena memory
+        outb = torch.empty(total * ncls, dtype=torch.float32, device=dev)
         bits = torch.empty(total, dtype=torch.uint8, device=dev)
-        S.check(S.lib.sis3d_mask_select(S.ptr(y.t), S.ptr(d_offs), S.ptr(d_cls), nk, ncls, C.c_int64(total),
-                                        S.f32(cfg.MASK_THRESH), None, S.ptr(bits), S.stream()), "mask_select")
-        if extras is not None:
-            extras.update(mask_bits=bits, mask_offsets=offs, mask_sizes=sizes)
-        return _MaskList(y.t, offs, sizes, ncls)
+        a.masks, a.bits, a.thresh = outb.data_ptr(), bits.data_ptr(), float(cfg.MASK_THRESH)
+        if extras is not None:  # the scene loop reads the thresholded masks back: ONE small D2H, queued by the same call
+            pin = self._ws("bits_host", total, torch.uint8, dev, pinned=True)
+            a.bits_host = pin.data_ptr()
+            extras.update(mask_bits=bits, mask_offsets=offs, mask_sizes=sizes, bits_pin=pin[:total])
+        tok = self._rec("mask_stage")
+        S.check(S.lib.sis3d_mask_stage_launch(C.byref(plan), C.c_void_p(stage.data_ptr()), C.byref(a), S.stream()), "mask_stage")
+        self._rec_end(tok)
+        return _MaskList(outb.view(total, ncls), offs, sizes, ncls)
 
     # ------------------------------------------------------------------ forward
     _carve_layouts = {}
@@ -762,15 +731,21 @@ class Network(nn.Module):
             d = n.__dict__  # plain attribute writes: nn.Module.__setattr__ costs ~5 us each
             self.saved = (d["_graphs"], d["_arena"])
             d["_graphs"], d["_arena"] = sl["graphs"], sl["arena"]
-            self.ctx = torch.cuda.stream(sl["stream"]) if sl["stream"] is not None else None
-            if self.ctx is not None:
-                self.ctx.__enter__()
-            self.old_pin = S.pin_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            self.prev = None
+            if sl["stream"] is not None:  # set_stream is several times cheaper than the torch.cuda.stream() context manager
+                self.prev = torch.cuda.current_stream()
+                torch.cuda.set_stream(sl["stream"])
+                handle = sl.get("handle")
+                if handle is None:
+                    handle = sl["handle"] = C.c_void_p(sl["stream"].cuda_stream)
+            else:
+                handle = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            self.old_pin = S.pin_stream(handle)
 
         def __exit__(self, *exc):
             S.pin_stream(self.old_pin)
-            if self.ctx is not None:
-                self.ctx.__exit__(*exc)
+            if self.prev is not None:
+                torch.cuda.set_stream(self.prev)
             d = self.net.__dict__
             d["_graphs"], d["_arena"] = self.saved
 
@@ -883,12 +858,9 @@ class Network(nn.Module):
                     extras = {}
                     P["mask_pred"] = [self._mask_branch(h["scene_t"], det_host, n, extras)]
                     P["detections_host"] = det_host
+                    if "bits_pin" in extras:  # thresholded predicted-class masks -> pinned host (queued by the mask stage)
+                        h["bits_pin"] = extras.pop("bits_pin")
                     P.update(extras)
-                    if "mask_bits" in extras:  # thresholded predicted-class masks -> pinned host, asynchronously
-                        bits = extras["mask_bits"]
-                        pin = self._ws("bits_host", bits.numel(), torch.uint8, bits.device, pinned=True)
-                        pin.copy_(bits, non_blocking=True)
-                        h["bits_pin"] = pin
             h["ev_done"] = torch.cuda.Event()
             h["ev_done"].record()
         h["P"] = P

@@ -318,7 +318,9 @@ def main():
     out = {
         "metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "tf32 (3x3x3 convs on tcgen05, fp32 accumulate) + f32" if math == "tf32" else "f32",
+        "dtype": {"tf32": "tf32 (convs on tcgen05, fp32 accumulate) + f32",
+                  "mixed": "tf32 (static-stage convs) / f16 operands (mask-stage convs) on tcgen05, fp32 accumulate, + f32",
+                  "fp16": "f16 operands (convs on tcgen05, fp32 accumulate) + f32"}.get(math, "f32"),
         "data": "synthetic",
         "config": {"workload": "96x48x96 ScanNet-shape chunk, 5 views, full rpn_class_mask_5 TEST forward (cfg2)",
                    "conv_math": math, "inputs": "seeded synthetic TSDF + ENet-shaped features/depth/poses; seeded synthetic weights",

@@ -258,6 +258,31 @@ typedef struct sis3d_mask_plan {
 int sis3d_mask_plan_build(const float *h_det, int n, int X, int Y, int Z, int ncls, int use_canvas, void *h_blob,
                           size_t capacity, sis3d_mask_plan *plan);
 
+/* One host call for every launch of a scene's ragged mask stage: H2D of the planner's tables, canvas zeroing, the six
+ * layers (math 0: fp32 CUDA-core kernel on compact crops; 1: TF32 tcgen05 on the canvas; 2: fp16-operand tcgen05), the
+ * predicted-class select and (bits_host != NULL) the D2H of the thresholded masks.  w_first / w_last: sis3d_pack_conv_weight
+ * of geometry.0 / geometry.10; w_mid[i]: geometry.{2,4,6,8} packed for `math` (pack_conv_weight / _tc / _tc_f16).
+ * canvas_bytes >= 2 layers x voxels x 64 channels in the operand type; SIS3D_EWORKSPACE otherwise. */
+typedef struct sis3d_mask_stage {
+    const float *scene;            /* NCDHW [2][X][Y][Z] */
+    int32_t X, Y, Z, ncls, math, reserved;
+    const float *w_first, *w_last;
+    const void *w_mid[4];
+    void *tables;                  /* device, >= plan->bytes */
+    void *canvas;
+    size_t canvas_bytes;
+    float *canvas32;               /* math 2 only: fp32 output of the last 3x3x3 layer */
+    size_t canvas32_bytes;
+    float *masks;                  /* [total_voxels][ncls] sigmoid outputs */
+    uint8_t *bits;                 /* [total_voxels] thresholded predicted-class masks, or NULL */
+    uint8_t *bits_host;            /* pinned host destination for `bits`, or NULL */
+    float thresh;
+    int32_t reserved2;
+} sis3d_mask_stage;
+int sis3d_mask_stage_launch(const sis3d_mask_plan *plan, const void *h_blob, const sis3d_mask_stage *args, void *stream);
+/* cudaMemcpyAsync behind the C ABI (kind 1 H2D, 2 D2H, 3 D2D) for hosts that stage their own pinned buffers. */
+int sis3d_memcpy_async(void *dst, const void *src, size_t bytes, int kind, void *stream);
+
 /* Predicted-class mask channel of every kept RoI, packed back to back, optionally thresholded to bits
  * (lib/model/trainval.py:900-908).  masks [total][ncls]; offs int64[n_crops+1] voxel offsets; cls int32[n_crops]. */
 int sis3d_mask_select(const float *masks, const int64_t *offs, const int32_t *cls, int n_crops, int ncls,
