@@ -643,7 +643,7 @@ class Network(nn.Module):
         tok = self._rec("mask_stage")
         S.check(S.lib.sis3d_mask_stage_launch(C.byref(plan), C.c_void_p(stage.data_ptr()), C.byref(a), S.stream()), "mask_stage")
         self._rec_end(tok)
-        return _MaskList(outb.view(total, ncls), offs, sizes, ncls)
+        return _MaskList(outb, offs, sizes, ncls)
 
     # ------------------------------------------------------------------ forward
     _carve_layouts = {}
