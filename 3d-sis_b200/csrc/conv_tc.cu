@@ -39,6 +39,7 @@ struct TcArgs {
     int tiles_y, tiles_z;
     int gemm_m, gemm_chunks_per_split;  // KS == 0 (plain GEMM y = x W^T, split-K over blockIdx.z)
     __half *out16;                      // optional fp16 twin of the output (same geometry as `out`); `out` may be null
+    const float *bias_mid;              // N2 > 0: bias of the 3x3x3 conv (added before the inner ReLU), or null
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -125,17 +126,27 @@ struct TcStages { static constexpr int value = BN >= 128 ? 4 : 3; };
 // stage count per kernel flavour: the 3x3x3 stages are 3x bigger (slab + three weight tiles)
 template <int BN, int KS, int ROWB>
 struct TcStagesOf { static constexpr int value = KS == 3 ? (BN >= 128 ? 3 : 2) : TcStages<BN>::value; };  // narrow 3x3x3 layers: 2 stages so 2-3 CTAs share an SM
-template <int BN, int KS, int ROWB, int BY>
+template <int BN, int KS, int ROWB, int BY, int N2 = 0>
 constexpr size_t tc_smem_bytes() {
     return (size_t)TcStagesOf<BN, KS, ROWB>::value *
-               ((KS == 3 ? (16 / BY + 2) * BY * TC_BZ : TC_BM) * ROWB + (KS == 3 ? 3 : 1) * BN * ROWB) + 1024 + 256;
+               ((KS == 3 ? (16 / BY + 2) * BY * TC_BZ : TC_BM) * ROWB + (KS == 3 ? 3 : 1) * BN * ROWB) +
+           (size_t)N2 * 128 * (BN / 32) + 1024 + 256;
 }
+constexpr int tc_tmem_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
 // EB = operand element bytes: 4 -> fp32 storage, kind::tf32;  2 -> fp16 storage, kind::f16 (same 11-bit significand,
 // half the operand bytes through L2).  ROWB = bytes of one K slice row in shared memory (128, or 64 for C_in = 32 in fp16).
-template <int BN, int KS, int EB = 4, int ROWB = 128, int BY = 2>
+//
+// N2 > 0 (KS = 3, TF32 only) fuses the bottleneck's trailing 1x1 convolution (lib/nets/backbones.py:28-40: conv2 -> relu ->
+// conv3 -> +x -> relu): the ReLU'd 128 x BN accumulator is written back to shared memory as a K-major SWIZZLE_128B operand
+// (aliasing the drained pipeline stages), multiplied by W3[N2][BN] (its own TMA tile, fetched at kernel start) into a second
+// TMEM accumulator, and only that N2-wide result -- plus residual and ReLU -- goes to global memory.  The BN-wide
+// intermediate never leaves the SM; operand values and summation order equal the two-kernel path bit for bit.
+template <int BN, int KS, int EB = 4, int ROWB = 128, int BY = 2, int N2 = 0>
 __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                              const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+                                                              const __grid_constant__ CUtensorMap tmB,
+                                                              const __grid_constant__ CUtensorMap tmB2, const TcArgs a) {
+    static_assert(N2 == 0 || (KS == 3 && EB == 4 && ROWB == 128), "conv3 fusion: TF32 3x3x3 kernels only");
     constexpr int KC = ROWB / EB;            // channels per pipeline stage
     constexpr int TC_BY = BY, TC_BX = 16 / BY;  // brick: BY = 2 -> 8x2x8 (whole volumes), BY = 4 -> 4x4x8 (small RoI crops)
     // 3x3x3: one stage = one (dy, dz) pair: an x-halo slab of (8+2) x-planes (160 rows) serves the three x-taps --
@@ -148,20 +159,26 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
     constexpr int TC_STAGES = TcStagesOf<BN, KS, ROWB>::value;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B needs 1024 B alignment
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + TC_STAGES * STAGE_BYTES);
+    constexpr int B2_BYTES = N2 * 128 * (BN / 32);  // W3 as BN/32 K slices of [N2 rows][32 ch]
+    constexpr int TMEM_COLS = tc_tmem_cols(BN + N2);
+    uint8_t *smem_b2 = smem + TC_STAGES * STAGE_BYTES;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_b2 + B2_BYTES);
     uint64_t *empty = full + TC_STAGES;
     uint64_t *acc_ready = empty + TC_STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_ready + 1);
+    uint64_t *b2_full = acc_ready + 1, *acc2_ready = acc_ready + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_ready + 3);
 
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         for (int i = 0; i < TC_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
         mbar_init(acc_ready, 1);
+        mbar_init(b2_full, 1);
+        mbar_init(acc2_ready, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {  // one full warp allocates BN TMEM columns (power of two >= 32)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -193,6 +210,11 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
 
     if (threadIdx.x == 0) {
         // ===== TMA producer =====
+        if constexpr (N2 > 0) {
+            mbar_expect_tx(b2_full, B2_BYTES);
+#pragma unroll
+            for (int kc = 0; kc < BN / 32; ++kc) tma_load_2d(smem_b2 + kc * N2 * 128, &tmB2, b2_full, kc * 32, 0);
+        }
         for (int it = 0; it < total; ++it) {
             const int s = it % TC_STAGES;
             const uint32_t ph = (it / TC_STAGES) & 1;
@@ -261,7 +283,7 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+        if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
         return;
     }
 
@@ -269,6 +291,50 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
     mbar_wait(acc_ready, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int r = threadIdx.x;
+    uint32_t acc_col = 0;  // first TMEM column of the accumulator the store loop reads
+    if constexpr (N2 > 0) {
+        // conv2's tile -> ReLU -> shared memory as the A operand of the 1x1 conv: row r, 16-byte chunk j of K slice kc at
+        // kc*16 KB + r*128 + ((j ^ (r & 7)) << 4)  (the canonical SWIZZLE_128B K-major layout TMA would have produced)
+        uint8_t *a2 = smem;  // aliases the pipeline stages: every TMA write landed and every MMA reading them retired
+#pragma unroll 1
+        for (int kc = 0; kc < BN / 32; ++kc) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(kc * 32), v);
+            uint8_t *row = a2 + kc * (TC_BM * 128) + r * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                if (a.bias_mid) {
+                    const float4 b = __ldg(reinterpret_cast<const float4 *>(a.bias_mid + kc * 32 + 4 * j));
+                    o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                }
+                *reinterpret_cast<float4 *>(row + ((j ^ (r & 7)) << 4)) =
+                    make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA's async proxy
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (threadIdx.x == 32) {
+            const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N2 >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            mbar_wait(b2_full, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa2 = smem_u32(a2), sb2 = smem_u32(smem_b2);
+#pragma unroll
+            for (int kc = 0; kc < BN / 32; ++kc)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_tf32(tmem_base + BN, umma_desc<128>(sa2 + kc * (TC_BM * 128) + k * 32),
+                              umma_desc<128>(sb2 + kc * (N2 * 128) + k * 32), idesc2, (kc | k) ? 1u : 0u);
+            umma_commit(acc2_ready);
+        }
+        __syncwarp();
+        mbar_wait(acc2_ready, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        acc_col = BN;
+    }
+    constexpr int NOUT = N2 > 0 ? N2 : BN;
     const int vz = z0 + (r & (TC_BZ - 1)), vy = y0 + ((r / TC_BZ) % TC_BY), vx = x0 + r / (TC_BZ * TC_BY);
     const bool valid = vx < x1 && vy < y1 && vz < z1;
     const int64_t vox = ((int64_t)vx * a.Y + vy) * a.Z + vz;
@@ -276,9 +342,9 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
     __half *hrow = a.out16 ? a.out16 + vox * a.out_ld + a.out_coff + n0 : nullptr;
     const float *rrow = a.res ? a.res + vox * a.res_ld + a.res_coff + n0 : nullptr;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = 0; c < NOUT / 32; ++c) {
         float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc_col + (uint32_t)(c * 32), v);
         if (valid) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -305,7 +371,7 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
 }
 
 __global__ void gemm_splitk_reduce_kernel(const float *part, int splits, int64_t split_stride, const float *bias, float *y, int M,
@@ -344,17 +410,18 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-template <int BN, int KS, int EB = 4, int ROWB = 128, int BY = 2>
-static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcArgs &a, int n_tiles, cudaStream_t s) {
-    const size_t smem = tc_smem_bytes<BN, KS, ROWB, BY>();
+template <int BN, int KS, int EB = 4, int ROWB = 128, int BY = 2, int N2 = 0>
+static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcArgs &a, int n_tiles, cudaStream_t s,
+                     const CUtensorMap *tmB2 = nullptr) {
+    const size_t smem = tc_smem_bytes<BN, KS, ROWB, BY, N2>();
     static bool attr_done = false;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(conv3d_k3_tc_kernel<BN, KS, EB, ROWB, BY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(conv3d_k3_tc_kernel<BN, KS, EB, ROWB, BY, N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return SIS3D_ELAUNCH;
         attr_done = true;
     }
-    dim3 grid(n_tiles, a.cout / BN);
-    conv3d_k3_tc_kernel<BN, KS, EB, ROWB, BY><<<grid, 128, smem, s>>>(tmA, tmB, a);
+    dim3 grid(n_tiles, N2 > 0 ? 1 : a.cout / BN);
+    conv3d_k3_tc_kernel<BN, KS, EB, ROWB, BY, N2><<<grid, 128, smem, s>>>(tmA, tmB, tmB2 ? *tmB2 : tmB, a);
     return finish_launch();
 }
 
@@ -453,6 +520,60 @@ extern "C" int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const floa
     }
 }
 
+// ---- bottleneck tail: 3x3x3 conv (cin -> cmid) + ReLU + 1x1 conv (cmid -> cout) + residual + act, one kernel ----------------
+extern "C" int sis3d_conv3d_k3_tc_fused_supported(int cin, int cmid, int cout) {
+    return (cin % TC_KC == 0 && ((cmid == 32 && (cout == 32 || cout == 64)) || (cmid == 64 && cout == 128))) ? 1 : 0;
+}
+extern "C" int sis3d_conv3d_k3_tc_fused(const float *in, const float *w2_tc, const float *bias2, const float *w3_tc,
+                                        const float *bias3, const float *residual, int res_ld, int res_coff, float *out,
+                                        int out_ld, int out_coff, int X, int Y, int Z, int cin, int cmid, int cout, int act,
+                                        void *stream) {
+    if (!in || !w2_tc || !w3_tc || !out || X <= 0 || Y <= 0 || Z <= 0) return SIS3D_EINVAL;
+    if (!sis3d_conv3d_k3_tc_fused_supported(cin, cmid, cout)) return SIS3D_EUNSUPPORTED;
+    if (((uintptr_t)in | (uintptr_t)w2_tc | (uintptr_t)w3_tc | (uintptr_t)out) & 15) return SIS3D_EINVAL;
+    if ((out_ld | out_coff | res_ld | res_coff) & 3) return SIS3D_EINVAL;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return SIS3D_EUNSUPPORTED;
+    const int by = 2, bx = 8;
+    CUtensorMap tmA, tmB, tmB2;
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X};
+        cuuint64_t strides[3] = {(cuuint64_t)cin * 4, (cuuint64_t)Z * cin * 4, (cuuint64_t)Y * Z * cin * 4};
+        cuuint32_t box[4] = {TC_KC, TC_BZ, (cuuint32_t)by, (cuuint32_t)(bx + 2)};
+        if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return SIS3D_EINVAL;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)27 * cin, (cuuint64_t)cmid};
+        cuuint64_t strides[1] = {(cuuint64_t)27 * cin * 4};
+        cuuint32_t box[2] = {TC_KC, (cuuint32_t)cmid};
+        if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)w2_tc, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return SIS3D_EINVAL;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)cmid, (cuuint64_t)cout};
+        cuuint64_t strides[1] = {(cuuint64_t)cmid * 4};
+        cuuint32_t box[2] = {TC_KC, (cuuint32_t)cout};
+        if (enc(&tmB2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)w3_tc, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return SIS3D_EINVAL;
+    }
+    TcArgs a;
+    a.bias = bias3; a.bias_mid = bias2; a.res = residual; a.out = out; a.tiles = nullptr; a.out16 = nullptr;
+    a.X = X; a.Y = Y; a.Z = Z; a.cin = cin; a.cout = cout; a.act = act;
+    a.out_ld = out_ld; a.out_coff = out_coff; a.res_ld = res_ld; a.res_coff = res_coff;
+    a.tiles_y = cdiv(Y, by); a.tiles_z = cdiv(Z, TC_BZ);
+    a.gemm_m = 0; a.gemm_chunks_per_split = 0;
+    const int n_tiles = cdiv(X, bx) * a.tiles_y * a.tiles_z;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cmid == 32 && cout == 32) return launch_tc<32, 3, 4, 128, 2, 32>(tmA, tmB, a, n_tiles, s, &tmB2);
+    if (cmid == 32 && cout == 64) return launch_tc<32, 3, 4, 128, 2, 64>(tmA, tmB, a, n_tiles, s, &tmB2);
+    return launch_tc<64, 3, 4, 128, 2, 128>(tmA, tmB, a, n_tiles, s, &tmB2);
+}
+
 // ---- y[M][N] = act(x[M][K] . w[N][K]^T + b): fully connected layer on the tensor cores (TF32), split-K ------------
 static int gemm_tc_splits(int M, int N, int K) {
     const int tiles = cdiv(M, TC_BM) * (N / (N >= 128 ? 128 : N));
@@ -500,15 +621,15 @@ extern "C" int sis3d_linear_tc(const float *x, const float *w_nk, const float *b
     if (BN == 32) {
         const size_t smem = (size_t)TcStages<32>::value * (TC_A_BYTES + 32 * 128) + 1280;
         cudaFuncSetAttribute(conv3d_k3_tc_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        conv3d_k3_tc_kernel<32, 0><<<grid, 128, smem, s>>>(tmA, tmB, a);
+        conv3d_k3_tc_kernel<32, 0><<<grid, 128, smem, s>>>(tmA, tmB, tmB, a);
     } else if (BN == 64) {
         const size_t smem = (size_t)TcStages<64>::value * (TC_A_BYTES + 64 * 128) + 1280;
         cudaFuncSetAttribute(conv3d_k3_tc_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        conv3d_k3_tc_kernel<64, 0><<<grid, 128, smem, s>>>(tmA, tmB, a);
+        conv3d_k3_tc_kernel<64, 0><<<grid, 128, smem, s>>>(tmA, tmB, tmB, a);
     } else {
         const size_t smem = (size_t)TcStages<128>::value * (TC_A_BYTES + 128 * 128) + 1280;
         cudaFuncSetAttribute(conv3d_k3_tc_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        conv3d_k3_tc_kernel<128, 0><<<grid, 128, smem, s>>>(tmA, tmB, a);
+        conv3d_k3_tc_kernel<128, 0><<<grid, 128, smem, s>>>(tmA, tmB, tmB, a);
     }
     gemm_splitk_reduce_kernel<<<cdiv(M * N, 256), 256, 0, s>>>((const float *)workspace, splits, (int64_t)M * N, bias, y, M, N, act);
     rc = finish_launch(2);

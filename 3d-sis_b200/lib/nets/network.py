@@ -106,6 +106,7 @@ class Network(nn.Module):
         self._branches = os.environ.get("SIS3D_BRANCHES", "1") != "0"
         self._replayed_kernels = 0  # libsis3d kernels executed through CUDA-graph replays
         self._sparse_color = os.environ.get("SIS3D_SPARSE_COLOR", "1") != "0"
+        self._fuse_bneck = os.environ.get("SIS3D_FUSE_BNECK", "1") != "0"
         self._pack_dirty = True
         self._arena = {}  # grow-only device/pinned workspaces for the ragged (per-scene sized) stage
         self._use_graph = os.environ.get("SIS3D_CUDA_GRAPH", "1") != "0"
@@ -367,8 +368,22 @@ class Network(nn.Module):
         activations exist only as fp16 (they feed tensor-core layers only); the block output is fp32 (+ fp16 twin when it
         is a dense tensor, for the next block's first conv)."""
         y = self._conv(x, name + ".conv1", act=1, want32=False, want16=True)
-        y = self._conv(y, name + ".conv2", act=1, want32=False, want16=True)
-        return self._conv(y, name + ".conv3", act=1, residual=x, out=out, want32=True, want16=True)
+        n2, n3 = name + ".conv2", name + ".conv3"
+        if self._math == "tf32" and self._fuse_bneck and n2 in self._packed_tc and n3 in self._packed_tc and y.t is not None:
+            _, _, cmid, cin, _ = self._packed[n2]
+            cout = self._packed[n3][2]
+            if y.ld == y.C and y.coff == 0 and S.lib.sis3d_conv3d_k3_tc_fused_supported(cin, cmid, cout):
+                # conv2 + conv3 (+x, ReLU) in one tcgen05 kernel: the cmid-wide activation never leaves the SM
+                if out is None:
+                    out = Act(torch.empty(*y.dims, cout, dtype=torch.float32, device=y.t.device), y.dims, cout)
+                tok = self._rec(f"conv_tc_fused[{name}]")
+                S.check(S.lib.sis3d_conv3d_k3_tc_fused(S.ptr(y.t), S.ptr(self._packed_tc[n2]), S.ptr(self._packed[n2][1]),
+                                                       S.ptr(self._packed_tc[n3]), S.ptr(self._packed[n3][1]), S.ptr(x.t), x.ld, x.coff, S.ptr(out.t), out.ld, out.coff, *y.dims, cin,
+                                                       cmid, cout, 1, S.stream()), f"conv3d_k3_tc_fused[{name}]")
+                self._rec_end(tok)
+                return out
+        y = self._conv(y, n2, act=1, want32=False, want16=True)
+        return self._conv(y, n3, act=1, residual=x, out=out, want32=True, want16=True)
 
     def _pool(self, x: Act, out: Act = None):
         if out is None:

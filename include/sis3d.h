@@ -176,6 +176,16 @@ int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const float *bias, co
                        int res_ld, int res_coff, float *out, int out_ld, int out_coff, int X, int Y,
                        int Z, int cin, int cout, int ks, const int32_t *tiles, int n_tiles, int act, void *stream);
 
+/* Bottleneck tail in ONE kernel (lib/nets/backbones.py:28-40: conv2 3x3x3 (+bias2) -> ReLU -> conv3 1x1 (+bias3) -> + residual -> act;
+ * biases may be NULL):
+ * the cmid-wide intermediate stays in shared memory / TMEM.  w2_tc / w3_tc from sis3d_pack_conv_weight_tc (ks 3 / ks 1).
+ * Supported: cin % 32 == 0 and (cmid, cout) in {(32,32), (32,64), (64,128)}; results equal the two-kernel TF32 path
+ * bit for bit (same operand values, same accumulation order). */
+int sis3d_conv3d_k3_tc_fused_supported(int cin, int cmid, int cout);
+int sis3d_conv3d_k3_tc_fused(const float *in, const float *w2_tc, const float *bias2, const float *w3_tc, const float *bias3,
+                             const float *residual, int res_ld, int res_coff, float *out, int out_ld, int out_coff, int X,
+                             int Y, int Z, int cin, int cmid, int cout, int act, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * fp16-operand tensor-core path (tcgen05 kind::f16, fp32 accumulate): activations and weights are STORED as fp16 (same
  * 11-bit significand TF32 keeps, half the bytes through L2 -- the kernel is bound by operand feed).  in16 is a dense VC

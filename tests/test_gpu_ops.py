@@ -385,6 +385,48 @@ def test_conv3d_tc_tf32_vs_fp32(S, cin, cout, dims, bias, res, act, ks):
     assert rel < 2e-3 and err < 2e-2, f"rel {rel:.2e} max {err:.2e}"
 
 
+@pytest.mark.parametrize("cin,cmid,cout,dims,res", [(32, 32, 32, (17, 9, 11), True), (32, 32, 64, (48, 24, 48), True),
+                                                     (32, 32, 64, (9, 3, 5), False), (64, 64, 128, (24, 12, 24), True),
+                                                     (64, 64, 128, (7, 5, 6), True)])
+def test_conv3d_tc_fused_bottleneck_tail(S, cin, cmid, cout, dims, res):
+    """conv2 (3x3x3) -> ReLU -> conv3 (1x1) -> +x -> ReLU in one tcgen05 kernel: bit-identical to the two-kernel TF32 path
+    (same operand values and accumulation order), and within TF32 rounding of torch fp32."""
+    rng = np.random.default_rng(cin + cout + dims[0])
+    x = rng.standard_normal((1, cin) + dims).astype(np.float32)
+    w2 = (rng.standard_normal((cmid, cin, 3, 3, 3)) / np.sqrt(cin * 27)).astype(np.float32)
+    w3 = (rng.standard_normal((cout, cmid, 1, 1, 1)) / np.sqrt(cmid)).astype(np.float32)
+    r = rng.standard_normal((1, cout) + dims).astype(np.float32)
+    b2, b3 = rng.standard_normal(cmid).astype(np.float32), rng.standard_normal(cout).astype(np.float32)
+    ref = F.conv3d(F.relu(F.conv3d(torch.from_numpy(x), torch.from_numpy(w2), torch.from_numpy(b2), padding=1)), torch.from_numpy(w3),
+                   torch.from_numpy(b3))
+    if res:
+        ref = ref + torch.from_numpy(r)
+    ref = F.relu(ref)
+    xd = torch.from_numpy(x[0]).to(DEV).permute(1, 2, 3, 0).contiguous()
+    rd = torch.from_numpy(r[0]).to(DEV).permute(1, 2, 3, 0).contiguous() if res else None
+    w2d, w3d = torch.from_numpy(w2).to(DEV), torch.from_numpy(w3).to(DEV)
+    w2t, w3t = torch.empty(cmid, 27 * cin, device=DEV), torch.empty(cout, cmid, device=DEV)
+    S.check(S.lib.sis3d_pack_conv_weight_tc(S.ptr(w2d), cmid, cin, 3, S.ptr(w2t), S.stream()))
+    S.check(S.lib.sis3d_pack_conv_weight_tc(S.ptr(w3d), cout, cmid, 1, S.ptr(w3t), S.stream()))
+    assert S.lib.sis3d_conv3d_k3_tc_fused_supported(cin, cmid, cout) == 1
+    out = torch.full(dims + (cout + 4,), 7.0, device=DEV)
+    b2d, b3d = torch.from_numpy(b2).to(DEV), torch.from_numpy(b3).to(DEV)
+    S.check(S.lib.sis3d_conv3d_k3_tc_fused(S.ptr(xd), S.ptr(w2t), S.ptr(b2d), S.ptr(w3t), S.ptr(b3d), S.ptr(rd), cout if res else 0, 0,
+                                           S.ptr(out), cout + 4, 4, *dims, cin, cmid, cout, 1, S.stream()))
+    mid = torch.empty(dims + (cmid,), device=DEV)
+    two = torch.empty(dims + (cout,), device=DEV)
+    S.check(S.lib.sis3d_conv3d_k3_tc(S.ptr(xd), S.ptr(w2t), S.ptr(b2d), None, 0, 0, S.ptr(mid), cmid, 0, *dims, cin, cmid, 3, None, 0, 1,
+                                     S.stream()))
+    S.check(S.lib.sis3d_conv3d_k3_tc(S.ptr(mid), S.ptr(w3t), S.ptr(b3d), S.ptr(rd), cout if res else 0, 0, S.ptr(two), cout, 0, *dims, cmid,
+                                     cout, 1, None, 0, 1, S.stream()))
+    torch.cuda.synchronize()
+    assert torch.all(out[..., :4] == 7.0)
+    assert torch.equal(out[..., 4:], two), "fused kernel differs from the two-kernel path"
+    got = out[..., 4:].permute(3, 0, 1, 2).cpu()
+    rel = ((got - ref[0]).norm() / ref[0].norm()).item()
+    assert rel < 3e-3, f"rel {rel:.2e}"
+
+
 def test_conv3d_tc_tile_list(S):
     """Explicit tile list: two crops packed on a zero-separated canvas == per-crop zero-padded conv."""
     rng = np.random.default_rng(3)
