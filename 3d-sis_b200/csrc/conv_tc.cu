@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
     }
     const int n0 = blockIdx.y * BN;
     const int kchunks = a.cin / KC;
-    constexpr int TAPS = KS == 3 ? 9 : 1;  // pipeline steps per K slice: 9 (dy,dz) pairs for 3x3x3, else 1
+    constexpr int TAPS = KS == 3 ? 9 : KS == 2 ? 8 : 1;  // pipeline steps per K slice: 9 (dy,dz) pairs (3x3x3), 8 taps (2x2x2/s2), else 1
     int total = TAPS * kchunks, chunk0 = 0;
     if constexpr (KS == 0) {  // split-K GEMM: this CTA owns K chunks [chunk0, chunk0 + total)
         chunk0 = blockIdx.z * a.gemm_chunks_per_split;
@@ -228,6 +228,12 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
             } else if constexpr (KS == 1) {
                 tma_load_4d(sa, &tmA, full + s, kc * KC, z0, y0, x0);
                 tma_load_2d(sa + A_BYTES, &tmB, full + s, kc * KC, n0);
+            } else if constexpr (KS == 2) {
+                // 2x2x2 / stride 2: the tensor map traverses the input with element strides {1,2,2,2}, so the box that starts
+                // at input voxel (2 x0 + dx, 2 y0 + dy, 2 z0 + dz) lands as the 128 output rows of this brick for tap (dx,dy,dz)
+                const int dx = tap >> 2, dy = (tap >> 1) & 1, dz = tap & 1;
+                tma_load_4d(sa, &tmA, full + s, kc * KC, 2 * z0 + dz, 2 * y0 + dy, 2 * x0 + dx);
+                tma_load_2d(sa + A_BYTES, &tmB, full + s, tap * a.cin + kc * KC, n0);
             } else {
                 const int dy = tap / 3, dz = tap % 3;  // tap = (dy, dz) pair; the slab covers x0-1 .. x0+8
                 tma_load_4d(sa, &tmA, full + s, kc * KC, z0 + dz - 1, y0 + dy - 1, x0 - 1);
@@ -454,7 +460,7 @@ __global__ void cast_f16_kernel(const float *in, int in_ld, int in_coff, int64_t
 using namespace sis3d;
 
 extern "C" int sis3d_pack_conv_weight_tc(const float *w, int cout, int cin, int ks, float *w_tc, void *stream) {
-    if (!w || !w_tc || cout <= 0 || cin <= 0 || (ks != 1 && ks != 3)) return SIS3D_EINVAL;
+    if (!w || !w_tc || cout <= 0 || cin <= 0 || (ks != 1 && ks != 2 && ks != 3)) return SIS3D_EINVAL;
     const int taps = ks * ks * ks;
     const int64_t total = (int64_t)cout * taps * cin;
     pack_conv_weight_tc_kernel<<<(int)imin64(cdiv64(total, 256), 148 * 8), 256, 0, (cudaStream_t)stream>>>(w, cout, cin, taps, w_tc);
@@ -468,7 +474,8 @@ extern "C" int sis3d_conv3d_k3_tc_supported(int cin, int cout) {
 extern "C" int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const float *bias, const float *residual, int res_ld,
                                   int res_coff, float *out, int out_ld, int out_coff, int X, int Y, int Z, int cin, int cout,
                                   int ks, const int32_t *tiles, int n_tiles, int act, void *stream) {
-    if (!in || !w_tc || !out || X <= 0 || Y <= 0 || Z <= 0 || (ks != 1 && ks != 3)) return SIS3D_EINVAL;
+    if (!in || !w_tc || !out || X <= 0 || Y <= 0 || Z <= 0 || (ks != 1 && ks != 2 && ks != 3)) return SIS3D_EINVAL;
+    if (ks == 2 && (tiles || X < 2 || Y < 2 || Z < 2)) return SIS3D_EINVAL;
     const int taps = ks * ks * ks;
     // explicit tile lists (ragged RoI crops) use 4x4x8 bricks, whole volumes 8x2x8 (sis3d_conv3d_tc_brick)
     const int by = (tiles && ks == 3 && cout == 64 && cin % 64 == 0) ? 4 : 2, bx = 16 / by;
@@ -478,12 +485,15 @@ extern "C" int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const floa
     EncodeTiledFn enc = get_encode();
     if (!enc) return SIS3D_EUNSUPPORTED;
     const int BN = cout >= 128 ? 128 : cout;
+    const int sd = ks == 2 ? 2 : 1;                   // ks == 2 is the stride-2, pad-0 conv: X, Y, Z are the INPUT extents
+    const int Xo = X / sd, Yo = Y / sd, Zo = Z / sd;  // output extents (floor, as nn.Conv3d)
     CUtensorMap tmA, tmB;
     {
         cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X};
         cuuint64_t strides[3] = {(cuuint64_t)cin * 4, (cuuint64_t)Z * cin * 4, (cuuint64_t)Y * Z * cin * 4};
-        cuuint32_t box[4] = {TC_KC, TC_BZ, (cuuint32_t)by, (cuuint32_t)(ks == 3 ? bx + 2 : bx)};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
+        // with element strides the box is given in traversed elements: N loaded voxels = boxDim / stride
+        cuuint32_t box[4] = {TC_KC, (cuuint32_t)(TC_BZ * sd), (cuuint32_t)(by * sd), (cuuint32_t)((ks == 3 ? bx + 2 : bx) * sd)};
+        cuuint32_t estr[4] = {1, (cuuint32_t)sd, (cuuint32_t)sd, (cuuint32_t)sd};
         if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return SIS3D_EINVAL;
@@ -498,11 +508,11 @@ extern "C" int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const floa
             return SIS3D_EINVAL;
     }
     TcArgs a;
-    a.bias = bias; a.res = residual; a.out = out; a.tiles = tiles; a.out16 = nullptr;
-    a.X = X; a.Y = Y; a.Z = Z; a.cin = cin; a.cout = cout; a.act = act;
+    a.bias = bias; a.res = residual; a.out = out; a.tiles = tiles; a.out16 = nullptr; a.bias_mid = nullptr;
+    a.X = Xo; a.Y = Yo; a.Z = Zo; a.cin = cin; a.cout = cout; a.act = act;
     a.out_ld = out_ld; a.out_coff = out_coff; a.res_ld = res_ld; a.res_coff = res_coff;
-    a.tiles_y = cdiv(Y, by); a.tiles_z = cdiv(Z, TC_BZ);
-    if (!tiles) n_tiles = cdiv(X, bx) * a.tiles_y * a.tiles_z;
+    a.tiles_y = cdiv(Yo, by); a.tiles_z = cdiv(Zo, TC_BZ);
+    if (!tiles) n_tiles = cdiv(Xo, bx) * a.tiles_y * a.tiles_z;
     if (n_tiles <= 0) return SIS3D_OK;
     cudaStream_t s = (cudaStream_t)stream;
     if (ks == 3) {
@@ -511,6 +521,13 @@ extern "C" int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const floa
             case 32: return launch_tc<32, 3>(tmA, tmB, a, n_tiles, s);
             case 64: return launch_tc<64, 3>(tmA, tmB, a, n_tiles, s);
             default: return launch_tc<128, 3>(tmA, tmB, a, n_tiles, s);
+        }
+    }
+    if (ks == 2) {
+        switch (BN) {
+            case 32: return launch_tc<32, 2>(tmA, tmB, a, n_tiles, s);
+            case 64: return launch_tc<64, 2>(tmA, tmB, a, n_tiles, s);
+            default: return launch_tc<128, 2>(tmA, tmB, a, n_tiles, s);
         }
     }
     switch (BN) {

@@ -100,13 +100,14 @@ class Network(nn.Module):
         # (same 11-bit significand, half the L2 traffic), 'fp32' = CUDA-core exact path
         # 'mixed' = TF32 operands in the static stage, fp16-stored operands in the ragged mask stage, which is bound by
         # the L2->SM operand feed (profiles/): halving the operand bytes there is worth more than anywhere else
-        self.set_conv_math(os.environ.get("SIS3D_CONV_MATH", str(cfg.get("CONV_MATH", "tf32"))).lower())
+        self.set_conv_math(os.environ.get("SIS3D_CONV_MATH", str(cfg.get("CONV_MATH", "mixed"))).lower())
         self._graphs = {}
         self._slots = []
         self._branches = os.environ.get("SIS3D_BRANCHES", "1") != "0"
         self._replayed_kernels = 0  # libsis3d kernels executed through CUDA-graph replays
         self._sparse_color = os.environ.get("SIS3D_SPARSE_COLOR", "1") != "0"
         self._fuse_bneck = os.environ.get("SIS3D_FUSE_BNECK", "1") != "0"
+        self._tc_k2s2 = os.environ.get("SIS3D_TC_K2S2", "1") != "0"
         self._pack_dirty = True
         self._arena = {}  # grow-only device/pinned workspaces for the ragged (per-scene sized) stage
         self._use_graph = os.environ.get("SIS3D_CUDA_GRAPH", "1") != "0"
@@ -213,11 +214,11 @@ class Network(nn.Module):
             S.check(S.lib.sis3d_pack_conv_weight(S.ptr(w), cout, cin, ks, S.ptr(packed), S.stream()), "pack")
             b = params.get(base + ".bias")
             self._packed[base] = (packed, None if b is None else b.detach().float().contiguous(), cout, cin, ks)
-            if ks in (1, 3) and p.dim() == 5 and S.lib.sis3d_conv3d_k3_tc_supported(cin, cout):
+            if ks in (1, 2, 3) and p.dim() == 5 and S.lib.sis3d_conv3d_k3_tc_supported(cin, cout):
                 wtc = torch.empty(cout, ks ** 3 * cin, dtype=torch.float32, device=w.device)
                 S.check(S.lib.sis3d_pack_conv_weight_tc(S.ptr(w), cout, cin, ks, S.ptr(wtc), S.stream()), "pack_tc")
                 self._packed_tc[base] = wtc
-                if cin % 64 == 0 or cin == 32:
+                if ks != 2 and (cin % 64 == 0 or cin == 32):
                     w16 = torch.empty(cout, ks ** 3 * cin, dtype=torch.float16, device=w.device)
                     S.check(S.lib.sis3d_pack_conv_weight_tc_f16(S.ptr(w), cout, cin, ks, S.ptr(w16), S.stream()), "pack_f16")
                     self._packed_h[base] = w16
@@ -296,8 +297,11 @@ class Network(nn.Module):
         regions_given = regions
         dev = (x.t if x.t is not None else x.h).device
         f16 = self._math == "fp16"
-        tc_ok = (regions_given is None and stride == 1 and pad == (1 if ks == 3 else 0) and x.layout == "vc"
-                 and x.ld == x.C and x.coff == 0 and act in (0, 1))
+        if ks == 2:  # the 2x2x2 / stride-2 downsampling convs run on the tensor cores too (element-strided TMA boxes)
+            geom_ok = stride == 2 and pad == 0 and min(x.dims) >= 2 and self._tc_k2s2
+        else:
+            geom_ok = stride == 1 and pad == (1 if ks == 3 else 0)
+        tc_ok = (regions_given is None and geom_ok and x.layout == "vc" and x.ld == x.C and x.coff == 0 and act in (0, 1))
         if not f16:
             want32, want16 = True, False
         if out is None:

@@ -183,7 +183,7 @@ def main():
     from lib import _sis3d as S
     from test_gpu_forward import make_net
     from test_oracle_golden import CASES
-    math = os.environ.get("SIS3D_CONV_MATH", "tf32")
+    math = os.environ.get("SIS3D_CONV_MATH", "mixed")
     net, cfg = make_net(CASES["cfg2_96x48x96"], keep_debug=False, math=math)
 
     # 24 distinct chunks per rank rotate (24 x 6.9 MB = 166 MB > the 126 MB L2): host (pinned) and device copies

@@ -160,7 +160,9 @@ int sis3d_mlp_tail(const float *x1, int R, int d1, const float *w2, const float 
                    const float *bb, int nb, float *cls_score, float *bbox_pred, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Tensor-core path for the stride-1 layers, ks = 3 (pad 1) or ks = 1 (same call sites as sis3d_conv3d):
+ * Tensor-core path: ks = 3 (stride 1, pad 1), ks = 1, or ks = 2 (the 2x2x2 / stride-2 / pad-0 downsampling convs,
+ * lib/nets/backbones.py:182-205; X,Y,Z are then the INPUT extents, the output is [X/2][Y/2][Z/2][cout], tiles must be NULL;
+ * the A operand is fetched by TMA boxes with element strides {1,2,2,2}) -- same call sites as sis3d_conv3d:
  * tcgen05.mma kind::tf32 with fp32 accumulation in TMEM, operands staged by 4-D/2-D TMA boxes
  * (csrc/conv_tc.cu).  `in` is a dense VC tensor [X][Y][Z][cin]; w_tc comes from
  * sis3d_pack_conv_weight_tc ([cout][ks^3*cin]).  tiles == NULL covers the whole volume with 8x2x8 (x,y,z)

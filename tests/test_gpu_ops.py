@@ -215,14 +215,17 @@ def test_conv3d_regions_zero_pad_at_crop_border(S):
         torch.testing.assert_close(got, ref, atol=2e-5, rtol=1e-4)
 
 
-def test_maxpool3_exact(S):
-    x = torch.randn(1, 64, 9, 5, 7)
+@pytest.mark.parametrize("C,dims", [(64, (9, 5, 7)), (64, (48, 24, 48)), (128, (24, 12, 24)), (16, (17, 8, 3)), (8, (6, 9, 11)),
+                                    (64, (1, 1, 1))])
+def test_maxpool3_exact(S, C, dims):
+    """MaxPool3d(3,1,1): tiled kernel (C % 16 == 0) and the generic one, written into a channel slice of a wider tensor."""
+    x = torch.randn(1, C, *dims)
     ref = F.max_pool3d(x, 3, 1, 1)[0]
     xd = x[0].to(DEV).permute(1, 2, 3, 0).contiguous()
-    out = torch.zeros(9, 5, 7, 128, device=DEV)
-    S.check(S.lib.sis3d_maxpool3(S.ptr(xd), S.ptr(out), 128, 64, 9, 5, 7, 64, S.stream()))
-    assert torch.equal(out[..., 64:].permute(3, 0, 1, 2).cpu(), ref)
-    assert not out[..., :64].any()
+    out = torch.zeros(*dims, 2 * C, device=DEV)
+    S.check(S.lib.sis3d_maxpool3(S.ptr(xd), S.ptr(out), 2 * C, C, *dims, C, S.stream()))
+    assert torch.equal(out[..., C:].permute(3, 0, 1, 2).cpu(), ref)
+    assert not out[..., :C].any()
 
 
 # ---------------------------------------------------------------- projection
@@ -383,6 +386,29 @@ def test_conv3d_tc_tf32_vs_fp32(S, cin, cout, dims, bias, res, act, ks):
     err = (got - ref[0]).abs().max().item()
     rel = ((got - ref[0]).norm() / ref[0].norm()).item()
     assert rel < 2e-3 and err < 2e-2, f"rel {rel:.2e} max {err:.2e}"
+
+
+@pytest.mark.parametrize("cin,cout,dims", [(32, 64, (48, 24, 48)), (64, 64, (48, 24, 48)), (64, 64, (45, 27, 41)), (32, 32, (9, 5, 7)),
+                                           (64, 128, (16, 6, 18)), (32, 64, (2, 2, 2))])
+def test_conv3d_tc_k2s2(S, cin, cout, dims):
+    """2x2x2 / stride-2 conv on the tcgen05 kernel (element-strided TMA boxes), incl. odd extents (floor semantics)."""
+    rng = np.random.default_rng(cin + cout + dims[0])
+    x = rng.standard_normal((1, cin) + dims).astype(np.float32)
+    w = (rng.standard_normal((cout, cin, 2, 2, 2)) / np.sqrt(cin * 8)).astype(np.float32)
+    ref = F.relu(F.conv3d(torch.from_numpy(x), torch.from_numpy(w), stride=2))
+    xd = torch.from_numpy(x[0]).to(DEV).permute(1, 2, 3, 0).contiguous()
+    wd = torch.from_numpy(w).to(DEV)
+    wtc = torch.empty(cout, 8 * cin, device=DEV)
+    S.check(S.lib.sis3d_pack_conv_weight_tc(S.ptr(wd), cout, cin, 2, S.ptr(wtc), S.stream()))
+    od = tuple(d // 2 for d in dims)
+    out = torch.full(od + (cout + 4,), 7.0, device=DEV)
+    S.check(S.lib.sis3d_conv3d_k3_tc(S.ptr(xd), S.ptr(wtc), None, None, 0, 0, S.ptr(out), cout + 4, 4, *dims, cin, cout, 2, None, 0, 1,
+                                     S.stream()))
+    torch.cuda.synchronize()
+    assert torch.all(out[..., :4] == 7.0)
+    got = out[..., 4:].permute(3, 0, 1, 2).cpu()
+    rel = ((got - ref[0]).norm() / ref[0].norm()).item()
+    assert rel < 2e-3 and (got - ref[0]).abs().max().item() < 2e-2, f"rel {rel:.2e}"
 
 
 @pytest.mark.parametrize("cin,cmid,cout,dims,res", [(32, 32, 32, (17, 9, 11), True), (32, 32, 64, (48, 24, 48), True),

@@ -11,7 +11,7 @@ from test_oracle_golden import CASES
 from torch.profiler import profile, ProfilerActivity
 
 dev = torch.device("cuda", 0)
-net, cfg = make_net(CASES["cfg2_96x48x96"], keep_debug=False, math="tf32")
+net, cfg = make_net(CASES["cfg2_96x48x96"], keep_debug=False, math=os.environ.get("SIS3D_CONV_MATH", "mixed"))
 data, views = bench.case(1000)
 blobs = {"data": torch.from_numpy(data).to(dev), "id": ["x"],
          "nearest_images": {"images": [torch.from_numpy(views["feats"]).to(dev)], "depths": [torch.from_numpy(views["depths"]).to(dev)],
