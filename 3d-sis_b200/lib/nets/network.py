@@ -770,14 +770,19 @@ class Network(nn.Module):
 
     def _submit(self, blobs, killing_inds, slot):
         """Step 1 (async): input copies, static stage (graph replay), packed results -> pinned host (async D2H)."""
+        return self._run_static(self._stage_inputs(blobs, killing_inds, slot))
+
+    def _stage_inputs(self, blobs, killing_inds, slot):
+        """Step 1a (async): per-view constants on the host + the scene's input copies into the slot's static buffers.
+        The scene loop issues this one scene ahead of the graph replay so the H2D transfer hides behind compute."""
         self._ensure_packed()
         dev = next(self.parameters()).device
         data = blobs["data"]
         if data.shape[0] != 1:
             raise S.Sis3dError("batch size 1 only (as the reference's RoI pooling / proposal layer)")
         dims = tuple(int(v) for v in data.shape[2:])
-        h = dict(slot=slot, dims=dims, id=blobs["id"][0] if "id" in blobs else None, scene_info=data.shape[2:])
-        before = set(self._predictions) if self._keep_debug else None
+        h = dict(slot=slot, dims=dims, id=blobs["id"][0] if "id" in blobs else None, scene_info=data.shape[2:], blobs=blobs,
+                 killing_inds=killing_inds, dev=dev)
         with torch.no_grad(), Network._UseSlot(self, slot):
             lists = cfg.USE_IMAGES and "proj_ind_3d" in blobs
             use_graph = self._use_graph and not (self._keep_debug or self._prof is not None or lists)
@@ -790,6 +795,7 @@ class Network(nn.Module):
                 vp = proj.view_params(cfg.INTRINSIC, (w, hh), cfg.PROJ_DEPTH_MIN, cfg.PROJ_DEPTH_MAX, dims, None,
                                       imgs["poses"][0], imgs["world2grid"][0])
                 fused = dict(vp=vp, feats=imgs["images"][0], depths=torch.as_tensor(imgs["depths"][0]))
+            h.update(use_graph=use_graph, fused=fused)
             if use_graph:
                 nv = fused["feats"].shape[0] if fused else 0
                 fc = fused["feats"].shape[1] if fused else 0
@@ -801,9 +807,21 @@ class Network(nn.Module):
                     vph = self._ws("vp_host", fused["vp"].numel(), torch.float32, dev, pinned=True)
                     vph.copy_(fused["vp"].reshape(-1))
                     st["vp"].copy_(vph.view_as(st["vp"]), non_blocking=True)
-                    fdev = dict(vp=st["vp"], feats=st["feats"], depths=st["depths"])
+                    h["fdev"] = dict(vp=st["vp"], feats=st["feats"], depths=st["depths"])
                 else:
-                    fdev = None
+                    h["fdev"] = None
+                h["st"] = st
+        return h
+
+    def _run_static(self, h):
+        """Step 1b (async): static stage (graph replay) on the staged inputs, packed results -> pinned host (async D2H)."""
+        blobs, killing_inds, slot, dims, dev = h.pop("blobs"), h.pop("killing_inds"), h["slot"], h["dims"], h.pop("dev")
+        data = blobs["data"]
+        fused = h.pop("fused")
+        before = set(self._predictions) if self._keep_debug else None
+        with torch.no_grad(), Network._UseSlot(self, slot):
+            if h.pop("use_graph"):
+                st, fdev = h.pop("st"), h.pop("fdev")
                 if st["graph"] is None:
                     # eager warm-up (fills the region/constant caches, sets kernel attributes), then capture
                     self._static_stage(st["scene"], dims, blobs, None, fdev)
@@ -909,23 +927,30 @@ class Network(nn.Module):
         return self._finalize(self._launch_ragged(self._submit(blobs, killing_inds, self._slot(0))))
 
     def forward_pipelined(self, blobs_iter, mode="TEST"):
-        """Throughput form of the scene loop (lib/model/trainval.py:787-822): yields (blobs, predictions) in order
-        while overlapping scene i+1's input copies + static stage and scene i's ragged mask stage with scene
-        i-1's read-back, on three stream slots.  The yielded dict is only valid until the next iteration."""
+        """Throughput form of the scene loop (lib/model/trainval.py:787-822): yields (blobs, predictions) in order while
+        four scenes are in flight on four stream slots -- scene i+1: input H2D (issued one scene ahead so the transfer
+        hides behind compute); scene i: static stage (graph replay); scene i-1: ragged mask stage; scene i-2: read-back.
+        The yielded dict is only valid until the next iteration."""
         self._check_mode(mode)
         from collections import deque
-        q = deque()
+        q = deque()      # [blobs, handle, ragged_launched] of scenes whose static stage has been launched
+        staged = None    # (blobs, handle) of the scene whose inputs are uploading
         i = 0
-        depth = max(2, int(os.environ.get("SIS3D_PIPE_DEPTH", "3")))  # scenes in flight (= stream slots)
+        depth = max(3, int(os.environ.get("SIS3D_PIPE_DEPTH", "4")))  # scenes in flight (= stream slots)
         for blobs in blobs_iter:
-            q.append([blobs, self._submit(blobs, None, self._slot(1 + i % depth)), False])
+            if len(q) == depth - 1:  # frees the slot the new scene is about to use
+                b, h, _ = q.popleft()
+                yield b, self._finalize(h)
+            nxt = (blobs, self._stage_inputs(blobs, None, self._slot(1 + i % depth)))
             i += 1
+            if staged is not None:
+                q.append([staged[0], self._run_static(staged[1]), False])
+            staged = nxt
             if len(q) >= 2 and not q[-2][2]:
                 self._launch_ragged(q[-2][1])
                 q[-2][2] = True
-            if len(q) == depth:
-                b, h, _ = q.popleft()
-                yield b, self._finalize(h)
+        if staged is not None:
+            q.append([staged[0], self._run_static(staged[1]), False])
         while q:
             b, h, launched = q.popleft()
             if not launched:

@@ -205,7 +205,7 @@ def main():
         return net.forward(blobs, "TEST", None)
 
     def timed_loop(inputs, steps):
-        """K scenes through the scene-loop API (Network.forward_pipelined, 3 scenes in flight); every scene's
+        """K scenes through the scene-loop API (Network.forward_pipelined, 4 scenes in flight); every scene's
         detections and thresholded predicted-class masks are read back to the host.  CUDA events on the default
         stream bracket the region (it waits for the slot streams), barrier + synchronize on both sides."""
         d2h, vox, nroi, nmask = 0, 0, 0, 0
@@ -276,6 +276,19 @@ def main():
     ms_dev, launches, _, vox, nroi, nmask = timed_loop(dev_in, args.steps)
     ms_e2e, _, d2h, _, _, _ = timed_loop(host_in, args.steps)
     clocks.stop_flag = True
+    # pinned-host -> device copy bandwidth of this box (explains the gap between `value` and `e2e`)
+    probe_h = torch.empty(64 << 20, dtype=torch.uint8, pin_memory=True)
+    probe_d = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+    probe_d.copy_(probe_h, non_blocking=True)
+    torch.cuda.synchronize()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for _ in range(8):
+        probe_d.copy_(probe_h, non_blocking=True)
+    pe1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 8 * (64 << 20) / (pe0.elapsed_time(pe1) * 1e-3) / 1e9
+    del probe_h, probe_d
     lat_dev = latency(dev_in, min(args.steps, 30))
     lat_host = latency(host_in, min(args.steps, 30))
 
@@ -325,11 +338,11 @@ def main():
         "config": {"workload": "96x48x96 ScanNet-shape chunk, 5 views, full rpn_class_mask_5 TEST forward (cfg2)",
                    "conv_math": math, "inputs": "seeded synthetic TSDF + ENet-shaped features/depth/poses; seeded synthetic weights",
                    "l2": "24 distinct chunks per rank rotate: 166 MB of inputs > 126 MB L2 (no flush kernel)",
-                   "api": "Network.forward_pipelined (the scene loop; 3 scenes in flight on 3 streams)", "rois_per_step": nroi,
+                   "api": "Network.forward_pipelined (the scene loop; 4 scenes in flight on 4 streams, inputs uploaded one scene ahead)", "rois_per_step": nroi,
                    "mask_rois_per_step": nmask, "mask_voxels_per_step": vox, "chunks_per_rank": args.steps,
                    "parallelism": f"chunk-sharded dp{world}"},
         "e2e": {"value": e2e_v, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps,
+                "ms_per_step": ms_e2e / args.steps, "h2d_probe_gbs": round(h2d_gbs, 1),
                 "what": "same loop from pinned HOST buffers: H2D of scene+features+depth+poses and D2H of detections + "
                         "thresholded predicted-class masks inside the timed region"},
         "latency_ms": {"sync_forward_device_inputs": lat_dev, "sync_forward_host_inputs": lat_host,
