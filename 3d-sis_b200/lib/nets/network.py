@@ -108,6 +108,22 @@ class Network(nn.Module):
         self._sparse_color = os.environ.get("SIS3D_SPARSE_COLOR", "1") != "0"
         self._fuse_bneck = os.environ.get("SIS3D_FUSE_BNECK", "1") != "0"
         self._tc_k2s2 = os.environ.get("SIS3D_TC_K2S2", "1") != "0"
+        # host waits yield the core instead of spinning: with one process per GPU on a CPU-quota'd node, eight spinning
+        # waiters plus the Python loops would eat the whole quota (cgroup throttling stalls every rank at once)
+        # (spinning is ~9 % faster on an otherwise idle host, so it stays the default while cores are plentiful)
+        bs = os.environ.get("SIS3D_BLOCKING_SYNC")
+        if bs is None:
+            try:
+                cores = len(os.sched_getaffinity(0))
+                with open("/sys/fs/cgroup/cpu.max") as f:
+                    quota, period = f.read().split()
+                if quota != "max":
+                    cores = min(cores, max(1, int(quota) // int(period)))
+            except (OSError, ValueError, AttributeError):
+                cores = os.cpu_count() or 1
+            self._blocking_sync = cores < 3 * int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+        else:
+            self._blocking_sync = bs != "0"
         self._pack_dirty = True
         self._arena = {}  # grow-only device/pinned workspaces for the ragged (per-scene sized) stage
         self._use_graph = os.environ.get("SIS3D_CUDA_GRAPH", "1") != "0"
@@ -866,7 +882,7 @@ class Network(nn.Module):
                 det_pin = self._ws("det_host", outs["det"].numel(), torch.float32, dev, pinned=True).view_as(outs["det"])
                 det_pin.copy_(outs["det"], non_blocking=True)
                 h["det_pin"] = det_pin
-            h["ev_static"] = torch.cuda.Event()
+            h["ev_static"] = torch.cuda.Event(blocking=self._blocking_sync)
             h["ev_static"].record()
         if self._keep_debug:  # intermediate tensors the static stage left in _predictions (parity tests)
             h["debug"] = {k: v for k, v in self._predictions.items()
@@ -898,7 +914,7 @@ class Network(nn.Module):
                     if "bits_pin" in extras:  # thresholded predicted-class masks -> pinned host (queued by the mask stage)
                         h["bits_pin"] = extras.pop("bits_pin")
                     P.update(extras)
-            h["ev_done"] = torch.cuda.Event()
+            h["ev_done"] = torch.cuda.Event(blocking=self._blocking_sync)
             h["ev_done"].record()
         h["P"] = P
         return h
