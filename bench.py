@@ -162,11 +162,14 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--chunks-per-step", type=int, default=32,
+                    help="a step = one pass of the scene loop over this many chunks per rank (the pipeline holds 4 in flight)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="sis3d")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lean", action="store_true", help="profiling runs: skip the latency pass and the CPU baseline")
     ap.add_argument("--host-profile", type=int, default=0, help="cProfile N forwards -> gpurun_out/host_profile.txt")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -251,8 +254,9 @@ def main():
 
     for i in range(args.warmup):
         step(dev_in[i % n_in])
-    timed_loop(dev_in, max(6, args.warmup))   # captures the graphs of the three pipeline slots
-    timed_loop(host_in, max(6, args.warmup))
+    B = max(1, args.chunks_per_step)
+    timed_loop(dev_in, max(8, args.warmup * B))   # warm-up steps; also captures the graphs of the pipeline slots
+    timed_loop(host_in, max(8, args.warmup * B))
     if args.host_profile and rank == 0:
         import cProfile
         import io
@@ -273,8 +277,9 @@ def main():
     if rank == 0:
         clocks.start()
         time.sleep(0.3)
-    ms_dev, launches, _, vox, nroi, nmask = timed_loop(dev_in, args.steps)
-    ms_e2e, _, d2h, _, _, _ = timed_loop(host_in, args.steps)
+    n_chunks = args.steps * B  # chunks per rank inside each timed region
+    ms_dev, launches, _, vox, nroi, nmask = timed_loop(dev_in, n_chunks)
+    ms_e2e, _, d2h, _, _, _ = timed_loop(host_in, n_chunks)
     clocks.stop_flag = True
     # pinned-host -> device copy bandwidth of this box (explains the gap between `value` and `e2e`)
     probe_h = torch.empty(64 << 20, dtype=torch.uint8, pin_memory=True)
@@ -289,45 +294,49 @@ def main():
     torch.cuda.synchronize()
     h2d_gbs = 8 * (64 << 20) / (pe0.elapsed_time(pe1) * 1e-3) / 1e9
     del probe_h, probe_d
-    lat_dev = latency(dev_in, min(args.steps, 30))
-    lat_host = latency(host_in, min(args.steps, 30))
+    lat_dev = latency(dev_in, 30) if not args.lean else None
+    lat_host = latency(host_in, 30) if not args.lean else None
 
-    # per-kernel device time of the dominant kernel family, CUDA events on the launching stream
-    net._prof = {}
-    for i in range(min(args.steps, 5)):
-        step(dev_in[i % n_in])
+    # dominant tensor-core kernel, timed live: rpn_net_level{1,2} = 3x3x3 conv 128 -> 256 on the 24x12x24 level-1 grid through
+    # the C ABI, 40 back-to-back launches between two CUDA events on the launching stream (inputs 3.5 MB: L2-resident, as
+    # in the forward where the producer has just written them)
+    from lib import _sis3d as S
+    import ctypes as C
+    rx = torch.randn(24, 12, 24, 128, device=dev)
+    rw = torch.randn(256, 27 * 128, device=dev) * 0.02
+    rb = torch.zeros(256, device=dev)
+    ro = torch.empty(24, 12, 24, 256, device=dev)
+    sh = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def rpn_conv():
+        S.check(S.lib.sis3d_conv3d_k3_tc(S.ptr(rx), S.ptr(rw), S.ptr(rb), None, 0, 0, S.ptr(ro), 256, 0, 24, 12, 24, 128, 256, 3,
+                                         None, 0, 1, sh), "rpn conv")
+    for _ in range(5):
+        rpn_conv()
+    ke0, ke1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ke0.record()
+    for _ in range(40):
+        rpn_conv()
+    ke1.record()
     torch.cuda.synchronize()
-    prof = {k: (sum(a.elapsed_time(b) for a, b in v) / min(args.steps, 5), len(v) // min(args.steps, 5)) for k, v in net._prof.items()}
-    net._prof = None
+    rpn_ms = ke0.elapsed_time(ke1) / 40
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     hbm, tflops, which = peaks()
     per_step_ms = ms_dev / args.steps
-    value = world * args.steps / (ms_dev / 1e3)
-    e2e_v = world * args.steps / (ms_e2e / 1e3)
-    conv_ms = sum(v[0] for k, v in prof.items() if k.startswith("conv"))
-    top = sorted(prof.items(), key=lambda kv: -kv[1][0])[:6]
-    try:
-        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        with open(os.path.join(ROOT, "gpurun_out", f"kernel_times_{math}.json"), "w") as f:
-            json.dump({k: {"ms_per_step": v[0], "launch_groups_per_step": v[1]} for k, v in
-                       sorted(prof.items(), key=lambda kv: -kv[1][0])}, f, indent=1)
-    except Exception:
-        pass
+    per_chunk_ms = ms_dev / n_chunks
+    value = world * n_chunks / (ms_dev / 1e3)
+    e2e_v = world * n_chunks / (ms_e2e / 1e3)
     alg = ALG_BYTES + MASK_BYTES_PER_VOXEL * vox
-    kernel_ms = sum(v[0] for v in prof.values())
-    # dominant tensor-core kernel: rpn_net_level{1,2} = 3x3x3 conv 128->256 on 24x12x24 = 12.231 GFLOP per launch
-    rpn_ms = [v[0] for k, v in prof.items() if k.startswith("conv_tc[rpn_net_level")]
-    tensor_roof = None
-    if rpn_ms:
-        tf = 12.231e9 / (float(np.mean(rpn_ms)) * 1e-3) / 1e12
-        tensor_roof = {"bound": "tensor", "kernel": "conv3d_k3_tc_kernel<128,3> (rpn_net_level1/2, TF32 in, fp32 accumulate)",
-                       "achieved": tf, "peak": tflops / 2.0, "unit": "TFLOP/s", "frac": tf / (tflops / 2.0),
-                       "peak_note": "TF32 dense = half of the measured bf16 GEMM peak in MEASURED_PEAKS.json (no TF32 figure measured)",
-                       "flops_per_launch": 12.231e9, "ms_per_launch": float(np.mean(rpn_ms)),
-                       "traffic": 525.0e6, "traffic_note": "l1tex__m_xbar2l1tex_read_bytes of the <64> instance in profiles/ (L2->SM operand feed; DRAM ~12 MB)"}
+    tf = 12.231e9 / (rpn_ms * 1e-3) / 1e12
+    tensor_roof = {"bound": "tensor", "kernel": "conv3d_k3_tc_kernel<128,3> (rpn_net_level1/2: 3x3x3, 128 -> 256 ch, 24x12x24; TF32 in, fp32 accumulate)",
+                   "achieved": tf, "peak": tflops / 2.0, "unit": "TFLOP/s", "frac": tf / (tflops / 2.0),
+                   "peak_note": "TF32 dense = half of the measured bf16 GEMM peak in MEASURED_PEAKS.json (no TF32 figure measured)",
+                   "flops_per_launch": 12.231e9, "ms_per_launch": rpn_ms, "launches_timed": 40,
+                   "traffic": 7.1e6, "traffic_note": "dram__bytes_read+write per launch from the ncu --set full capture in profiles/ "
+                                                     "(operands are L2 hits: 271 MB cross the L2->SM crossbar per launch)"}
     out = {
         "metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -338,11 +347,12 @@ def main():
         "config": {"workload": "96x48x96 ScanNet-shape chunk, 5 views, full rpn_class_mask_5 TEST forward (cfg2)",
                    "conv_math": math, "inputs": "seeded synthetic TSDF + ENet-shaped features/depth/poses; seeded synthetic weights",
                    "l2": "24 distinct chunks per rank rotate: 166 MB of inputs > 126 MB L2 (no flush kernel)",
-                   "api": "Network.forward_pipelined (the scene loop; 4 scenes in flight on 4 streams, inputs uploaded one scene ahead)", "rois_per_step": nroi,
-                   "mask_rois_per_step": nmask, "mask_voxels_per_step": vox, "chunks_per_rank": args.steps,
+                   "api": "Network.forward_pipelined (the scene loop; 4 scenes in flight on 4 streams, inputs uploaded one scene ahead)", "chunks_per_step": B,
+                   "step": f"one pass of the scene loop over {B} chunks per rank", "rois_per_chunk": nroi,
+                   "mask_rois_per_chunk": nmask, "mask_voxels_per_chunk": vox, "chunks_per_rank": n_chunks,
                    "parallelism": f"chunk-sharded dp{world}"},
-        "e2e": {"value": e2e_v, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps, "h2d_probe_gbs": round(h2d_gbs, 1),
+        "e2e": {"value": e2e_v, "unit": "scenes/s", "h2d_bytes_per_step": h2d * B, "d2h_bytes_per_step": d2h * B,
+                "ms_per_step": ms_e2e / args.steps, "ms_per_chunk": ms_e2e / n_chunks, "h2d_probe_gbs": round(h2d_gbs, 1),
                 "what": "same loop from pinned HOST buffers: H2D of scene+features+depth+poses and D2H of detections + "
                         "thresholded predicted-class masks inside the timed region"},
         "latency_ms": {"sync_forward_device_inputs": lat_dev, "sync_forward_host_inputs": lat_host,
@@ -353,13 +363,12 @@ def main():
         "roofline": {"bound": "hbm", "achieved": alg * (value / world) / 1e9, "peak": hbm, "unit": "GB/s",
                      "frac": alg * (value / world) / 1e9 / hbm, "traffic": None, "peak_source": which,
                      "kernel": "whole forward = all libsis3d launches of one scene (graph replay + ragged mask stage)",
-                     "algorithmic_bytes_per_step": alg, "gpu_ms_per_step": per_step_ms,
-                     "eager_kernel_ms_per_step": kernel_ms, "conv_ms_per_step": conv_ms,
-                     "top_kernels_ms": {k: round(v[0], 4) for k, v in top}},
+                     "algorithmic_bytes_per_chunk": alg, "gpu_ms_per_chunk": per_chunk_ms,
+                     "note": "per-kernel times and shares: profiles/ (ncu launch list + --set full capture of the same command)"},
         "roofline_tensor_kernel": tensor_roof,
         "clocks": clocks.summary(),
     }
-    if not args.no_cpu_baseline and world == 1:
+    if not (args.no_cpu_baseline or args.lean) and world == 1:
         from oracle import port
         cores = best_threads(port, usable_cores())
         ocfg, w = port.make_cfg("scannet"), weights()
