@@ -944,15 +944,17 @@ class Network(nn.Module):
 
     def forward_pipelined(self, blobs_iter, mode="TEST"):
         """Throughput form of the scene loop (lib/model/trainval.py:787-822): yields (blobs, predictions) in order while
-        four scenes are in flight on four stream slots -- scene i+1: input H2D (issued one scene ahead so the transfer
-        hides behind compute); scene i: static stage (graph replay); scene i-1: ragged mask stage; scene i-2: read-back.
+        six scenes are in flight on six stream slots -- scene i+1: input H2D (issued one scene ahead so the transfer
+        hides behind compute); scenes i, i-1, i-2: static stage (three graph replays overlapping: one alone is a latency
+        chain of small grids); scene i-3: ragged mask stage; scene i-4: read-back.
         The yielded dict is only valid until the next iteration."""
         self._check_mode(mode)
         from collections import deque
         q = deque()      # [blobs, handle, ragged_launched] of scenes whose static stage has been launched
         staged = None    # (blobs, handle) of the scene whose inputs are uploading
         i = 0
-        depth = max(3, int(os.environ.get("SIS3D_PIPE_DEPTH", "4")))  # scenes in flight (= stream slots)
+        n_static = max(1, int(os.environ.get("SIS3D_PIPE_STATIC", "3")))  # static stages (graph replays) in flight at once
+        depth = max(n_static + 2, int(os.environ.get("SIS3D_PIPE_DEPTH", str(n_static + 3))))  # scenes in flight (= stream slots)
         for blobs in blobs_iter:
             if len(q) == depth - 1:  # frees the slot the new scene is about to use
                 b, h, _ = q.popleft()
@@ -962,9 +964,11 @@ class Network(nn.Module):
             if staged is not None:
                 q.append([staged[0], self._run_static(staged[1]), False])
             staged = nxt
-            if len(q) >= 2 and not q[-2][2]:
-                self._launch_ragged(q[-2][1])
-                q[-2][2] = True
+            # the mask stage of a scene needs its detections on the host: wait for the static stage launched n_static
+            # iterations ago, so that n_static graph replays overlap on the GPU (one alone is a latency chain of small grids)
+            if len(q) > n_static and not q[-n_static - 1][2]:
+                self._launch_ragged(q[-n_static - 1][1])
+                q[-n_static - 1][2] = True
         if staged is not None:
             q.append([staged[0], self._run_static(staged[1]), False])
         while q:

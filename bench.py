@@ -164,7 +164,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--chunks-per-step", type=int, default=32,
-                    help="a step = one pass of the scene loop over this many chunks per rank (the pipeline holds 4 in flight)")
+                    help="a step = one pass of the scene loop over this many chunks per rank (the pipeline holds 6 in flight)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="sis3d")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
@@ -208,7 +208,7 @@ def main():
         return net.forward(blobs, "TEST", None)
 
     def timed_loop(inputs, steps):
-        """K scenes through the scene-loop API (Network.forward_pipelined, 4 scenes in flight); every scene's
+        """K scenes through the scene-loop API (Network.forward_pipelined, 6 scenes in flight); every scene's
         detections and thresholded predicted-class masks are read back to the host.  CUDA events on the default
         stream bracket the region (it waits for the slot streams), barrier + synchronize on both sides."""
         d2h, vox, nroi, nmask = 0, 0, 0, 0
@@ -347,7 +347,7 @@ def main():
         "config": {"workload": "96x48x96 ScanNet-shape chunk, 5 views, full rpn_class_mask_5 TEST forward (cfg2)",
                    "conv_math": math, "inputs": "seeded synthetic TSDF + ENet-shaped features/depth/poses; seeded synthetic weights",
                    "l2": "24 distinct chunks per rank rotate: 166 MB of inputs > 126 MB L2 (no flush kernel)",
-                   "api": "Network.forward_pipelined (the scene loop; 4 scenes in flight on 4 streams, inputs uploaded one scene ahead)", "chunks_per_step": B,
+                   "api": "Network.forward_pipelined (the scene loop; 6 scenes in flight on 6 streams: inputs uploaded one scene ahead, 3 graph replays overlapping)", "chunks_per_step": B,
                    "step": f"one pass of the scene loop over {B} chunks per rank", "rois_per_chunk": nroi,
                    "mask_rois_per_chunk": nmask, "mask_voxels_per_chunk": vox, "chunks_per_rank": n_chunks,
                    "parallelism": f"chunk-sharded dp{world}"},
