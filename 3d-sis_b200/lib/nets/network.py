@@ -750,8 +750,9 @@ class Network(nn.Module):
         self._graphs[key] = st
         return st
 
-    # -- a forward is three host steps; `forward` runs them back to back, `forward_pipelined` overlaps them across
-    #    consecutive scenes on three stream slots (each slot owns its graphs, static buffers and arena)
+    # -- a forward is four host steps (stage inputs, static stage, ragged stage, finalize); `forward` runs them back to back,
+    #    `forward_pipelined` overlaps them across consecutive scenes on stream slots (each slot owns its graphs, static
+    #    buffers and arena)
     def _slot(self, i):
         while len(self._slots) <= i:
             self._slots.append(dict(stream=torch.cuda.Stream() if self._slots else None, graphs={}, arena={}))
