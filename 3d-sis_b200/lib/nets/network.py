@@ -205,12 +205,14 @@ class Network(nn.Module):
         self.__dict__["_mask_math"] = "fp16" if mode == "mixed" else mode
 
     def _ensure_packed(self):
+        d = self.__dict__
+        if not d["_pack_dirty"] and d["_packed_version"] is not None:  # per-scene fast path: no module traversal
+            return
         if not torch.cuda.is_available():
             raise S.Sis3dError("the sm_100a hot path needs a CUDA device (no CPU fallback)")
         if next(self.parameters()).device.type != "cuda":
             self.cuda()
-        if not self._pack_dirty and self._packed_version is not None:
-            return
+        d["_dev"] = next(self.parameters()).device
         v = self._version()
         self._pack_dirty = False
         if v == self._packed_version:
@@ -769,7 +771,9 @@ class Network(nn.Module):
             d["_graphs"], d["_arena"] = sl["graphs"], sl["arena"]
             self.prev = None
             if sl["stream"] is not None:  # set_stream is several times cheaper than the torch.cuda.stream() context manager
-                self.prev = torch.cuda.current_stream()
+                self.prev = d.get("_home_stream")  # the scene loop looks it up once, not three times per scene
+                if self.prev is None:
+                    self.prev = torch.cuda.current_stream()
                 torch.cuda.set_stream(sl["stream"])
                 handle = sl.get("handle")
                 if handle is None:
@@ -793,7 +797,7 @@ class Network(nn.Module):
         """Step 1a (async): per-view constants on the host + the scene's input copies into the slot's static buffers.
         The scene loop issues this one scene ahead of the graph replay so the H2D transfer hides behind compute."""
         self._ensure_packed()
-        dev = next(self.parameters()).device
+        dev = self.__dict__["_dev"]
         data = blobs["data"]
         if data.shape[0] != 1:
             raise S.Sis3dError("batch size 1 only (as the reference's RoI pooling / proposal layer)")
@@ -950,6 +954,14 @@ class Network(nn.Module):
         chain of small grids); scene i-3: ragged mask stage; scene i-4: read-back.
         The yielded dict is only valid until the next iteration."""
         self._check_mode(mode)
+        self._ensure_packed()
+        self.__dict__["_home_stream"] = torch.cuda.current_stream()  # restored after every slot switch of this loop
+        try:
+            yield from self._scene_loop(blobs_iter)
+        finally:
+            self.__dict__["_home_stream"] = None
+
+    def _scene_loop(self, blobs_iter):
         from collections import deque
         q = deque()      # [blobs, handle, ragged_launched] of scenes whose static stage has been launched
         staged = None    # (blobs, handle) of the scene whose inputs are uploading

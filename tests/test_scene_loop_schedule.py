@@ -1,4 +1,4 @@
-"""CPU: the scheduling logic of Network.forward_pipelined (order of the per-scene host steps, slot reuse safety,
+"""CPU: the scheduling logic of Network.forward_pipelined / _scene_loop (order of the per-scene host steps, slot reuse safety,
 overlap depth) with the GPU steps replaced by recorders."""
 import itertools
 
@@ -15,9 +15,6 @@ class _Recorder:
         self.slot_owner = {}   # slot index -> scene currently using it
         self.max_in_flight = 0
         self.in_flight = set()
-
-    def _check_mode(self, mode):
-        assert mode == "TEST"
 
     def _slot(self, i):
         return i
@@ -50,7 +47,7 @@ def test_scene_loop_order_and_slot_safety(monkeypatch, n_scenes, n_static):
     monkeypatch.setenv("SIS3D_PIPE_STATIC", str(n_static))
     monkeypatch.delenv("SIS3D_PIPE_DEPTH", raising=False)
     rec = _Recorder()
-    out = [(b, P["scene"]) for b, P in Network.forward_pipelined(rec, iter(range(n_scenes)))]
+    out = [(b, P["scene"]) for b, P in Network._scene_loop(rec, iter(range(n_scenes)))]
     assert out == [(i, i) for i in range(n_scenes)]          # every scene once, in order, with its own predictions
     assert not rec.slot_owner and not rec.in_flight          # everything drained
     assert rec.max_in_flight <= n_static + 3                 # staged + n_static replays + mask stage + read-back
