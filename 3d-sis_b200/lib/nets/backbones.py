@@ -84,7 +84,9 @@ class MaskBackbone(nn.Module):
 
     def forward(self, scene, imageft=None):
         """scene [1,2,w,h,l] crop (NCDHW) -> sigmoid mask [1,num_classes,w,h,l]."""
-        net = self._owner[0]
+        net = self._owner() if self._owner is not None else None
+        if net is None:
+            raise S.Sis3dError("mask_backbone is launched through its owning Network (which is gone)")
         net._ensure_packed()
         if scene.shape[0] != 1:
             raise S.Sis3dError("mask_backbone: batch size 1")

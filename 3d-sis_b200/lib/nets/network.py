@@ -14,6 +14,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -170,7 +171,9 @@ class Network(nn.Module):
         if cfg.USE_MASK:
             from lib.nets import backbones
             self.mask_backbone = getattr(backbones, cfg.MASK_BACKBONE)()
-            self.mask_backbone._owner = [self]
+            # weak back-reference: no parent<->child cycle, so a dropped Network (graphs, streams, arenas) is freed by
+            # reference counting right away instead of by a later cyclic GC pass in the middle of someone else's capture
+            self.mask_backbone._owner = weakref.ref(self)
         if cfg.USE_IMAGES and not cfg.USE_IMAGES_GT:
             # the 2D ENet encoder is upstream of the hot path; callers feed ENet-shaped
             # features (USE_IMAGES_GT semantics) or attach their own torch modules here.
