@@ -267,6 +267,10 @@ class Network(nn.Module):
                     self._packed_h[f"rpn_heads_level{lvl}"] = w16
         torch.cuda.current_stream().synchronize()
         self._packed_version = v
+        # captured graphs hold the addresses of the previous packed weights: drop them (re-captured on next use)
+        self.__dict__["_graphs"] = {}
+        for sl in self._slots:
+            sl["graphs"].clear()
 
     # ------------------------------------------------------------------ per-kernel timing hooks
     def _rec(self, name):
