@@ -486,3 +486,56 @@ def forward(cfg, w, data, views=None, timings=None, fma_mode=0):
     if timings is not None:
         timings.update(project=t1 - t0, backbone=t2 - t1, rpn=t3 - t2, roi_cls=t4 - t3, mask=t5 - t4, total=t5 - t0)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Row f2 (next): 2-D ENet encoder, images [n,3,256,328] -> features [n,128,32,41]
+# (lib/nets/enet.py:130-590 = create_enet modules 0..25; create_enet_for_3d, enet.py:697-715, keeps exactly those as
+# model_fixed + model_trainable; network.py:199-213 feeds their output to the back-projection).
+# Restated as a layer program; `params` = the tensors of the reference state_dict in its own order with the
+# num_batches_tracked counters dropped (tests/golden/enet_encoder.npz carries them as p000, p001, ...).
+# ------------------------------------------------------------------------------------------------
+_ENET_STAGE23 = [("reg", 1), ("reg", 2), ("asym", 5), ("reg", 4), ("reg", 1), ("reg", 8), ("asym", 5), ("reg", 16)]
+ENET_PROGRAM = ([("down", 16, 64, 0.01)] + [("reg", 16, 64, 0.01, 1)] * 4 + [("down", 32, 128, 0.1)] +
+                [(kind, 32, 128, 0.1, arg) for kind, arg in _ENET_STAGE23 * 2])
+ENET_BN_EPS = 1e-3  # nn.BatchNorm2d(C, 0.001, 0.1, True), enet.py:138
+
+
+def enet_encoder(params, images):
+    """Inference forward of the ENet encoder on CPU (eval-mode BatchNorm, Torch7-style Dropout2d that scales by
+    (1 - p) at inference, enet.py:89-95).  params: list of float32 tensors in reference order."""
+    it = iter(params)
+
+    def bn_prelu(x, prelu=True):
+        w, b, mean, var = next(it), next(it), next(it), next(it)
+        x = F.batch_norm(x, mean, var, w, b, False, 0.1, ENET_BN_EPS)
+        return F.prelu(x, next(it)) if prelu else x
+
+    x = images
+    w0, b0 = next(it), next(it)  # initial block: conv 3->13 k3 s2 p1 || 2x2 max-pool, concatenated (enet.py:132-137)
+    x = torch.cat((F.conv2d(x, w0, b0, stride=2, padding=1), F.max_pool2d(x, 2, 2)), 1)
+    x = bn_prelu(x)
+    for op in ENET_PROGRAM:
+        kind, mid, cout, p = op[0], op[1], op[2], op[3]
+        skip = x
+        if kind == "down":  # 2x2/s2 projection on the main branch, max-pool + zero channel padding on the skip
+            y = F.conv2d(x, next(it), None, stride=2)
+            skip = F.max_pool2d(x, 2, 2)
+            skip = torch.cat((skip, skip.new_zeros(skip.shape[0], cout - skip.shape[1], *skip.shape[2:])), 1)
+        else:
+            y = F.conv2d(x, next(it), None)
+        y = bn_prelu(y)
+        if kind == "asym":  # 1x5 (no bias) then 5x1 (bias), enet.py asymmetric bottlenecks
+            y = F.conv2d(y, next(it), None, padding=(0, 2))
+            w, b = next(it), next(it)
+            y = F.conv2d(y, w, b, padding=(2, 0))
+        else:
+            d = op[4] if kind == "reg" else 1
+            w, b = next(it), next(it)
+            y = F.conv2d(y, w, b, padding=d, dilation=d)
+        y = bn_prelu(y)
+        y = bn_prelu(F.conv2d(y, next(it), None), prelu=False) * (1.0 - p)
+        x = F.prelu(y + skip, next(it))
+    if next(it, None) is not None:
+        raise ValueError("enet_encoder: unused parameters (not the encoder's state_dict?)")
+    return x
