@@ -12,6 +12,7 @@ reference load unchanged.  Training mode is out of scope (inference-only hot pat
 from __future__ import annotations
 
 import ctypes as C
+import gc
 import math
 import os
 import weakref
@@ -857,10 +858,14 @@ class Network(nn.Module):
                     g = torch.cuda.CUDAGraph()
                     n0 = S.launch_count()
                     pin = S.pin_stream(None)  # capture runs on torch's capture stream
+                    gc_was_on = gc.isenabled()
+                    gc.disable()  # a cyclic-GC pass in the middle of a capture may free CUDA objects (illegal while capturing)
                     try:
                         with torch.cuda.graph(g):
                             st["outs"] = self._static_stage(st["scene"], dims, blobs, None, fdev)
                     finally:
+                        if gc_was_on:
+                            gc.enable()
                         S.pin_stream(pin)
                     st["graph"], st["n_kernels"] = g, S.launch_count() - n0
                 st["graph"].replay()
