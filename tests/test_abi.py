@@ -44,3 +44,38 @@ def test_state_dict_contract():
     want = synth.param_shapes()
     got = {k: tuple(v.shape) for k, v in net.state_dict().items()}
     assert got == dict(want)
+
+
+def test_host_side_queries_and_argument_checks():
+    """Pure host entry points answer without a GPU: capability queries, brick shapes, workspace sizes, EINVAL on nulls."""
+    import ctypes as C
+    from lib import _sis3d as S
+    L = S.lib
+    # tcgen05 conv support matrix (cin % 32 == 0, cout in {32, 64, 128k})
+    assert [L.sis3d_conv3d_k3_tc_supported(ci, co) for ci, co in ((32, 32), (64, 64), (128, 256), (2, 64), (32, 19), (48, 64))] \
+        == [1, 1, 1, 0, 0, 0]
+    # fused bottleneck tails: (cmid, cout) in {(32,32), (32,64), (64,128)}
+    assert [L.sis3d_conv3d_k3_tc_fused_supported(*t) for t in ((32, 32, 32), (32, 32, 64), (64, 64, 128), (32, 32, 128), (2, 32, 32))] \
+        == [1, 1, 1, 0, 0]
+    assert L.sis3d_linear_tc_supported(8192, 256) == 1 and L.sis3d_linear_tc_supported(100, 256) == 0
+    bx, by, bz = C.c_int32(), C.c_int32(), C.c_int32()
+    L.sis3d_conv3d_tc_brick(0, 3, 64, 64, C.byref(bx), C.byref(by), C.byref(bz))
+    assert (bx.value, by.value, bz.value) == (8, 2, 8)          # whole volumes
+    L.sis3d_conv3d_tc_brick(1, 3, 64, 64, C.byref(bx), C.byref(by), C.byref(bz))
+    assert (bx.value, by.value, bz.value) == (4, 4, 8)          # ragged tile lists of the mask head
+    assert bx.value * by.value * bz.value == 128
+    levels = (S.RpnLevel * 2)()
+    for lv, A in zip(levels, (3, 11)):
+        lv.grid[0], lv.grid[1], lv.grid[2], lv.num_anchors = 24, 12, 24, A
+    for fn, args in ((L.sis3d_nms_workspace_bytes, (400,)), (L.sis3d_rpn_workspace_bytes, (levels, 2, 400)),
+                     (L.sis3d_linear_workspace_bytes, (200, 256, 8192)), (L.sis3d_linear_tc_workspace_bytes, (200, 256, 8192))):
+        assert 0 < fn(*args) < (1 << 31)
+    assert L.sis3d_rpn_workspace_bytes(None, 2, 400) == 0 and L.sis3d_rpn_workspace_bytes(levels, 99, 400) == 0
+    # argument validation happens before any CUDA call
+    assert L.sis3d_nms(None, 4, C.c_float(0.5), None, None, None, None) == -1
+    assert L.sis3d_maxpool3(None, None, 64, 0, 4, 4, 4, 64, None) == -1
+    assert L.sis3d_conv3d_k3_tc_fused(None, None, None, None, None, None, 0, 0, None, 64, 0, 8, 8, 8, 32, 32, 64, 1, None) == -1
+    assert L.sis3d_mask_stage_launch(None, None, None, None) == -1
+    assert L.sis3d_memcpy_async(None, None, C.c_size_t(16), 1, None) == -1
+    assert L.sis3d_view_params_host(None, None, None, None, 1, 1, C.c_double(1), C.c_double(1), C.c_double(0), C.c_double(0), 41, 32,
+                                    C.c_double(0.1), C.c_double(4.0), 8, 8, 8, None) == -1
