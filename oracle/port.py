@@ -539,3 +539,54 @@ def enet_encoder(params, images):
     if next(it, None) is not None:
         raise ValueError("enet_encoder: unused parameters (not the encoder's state_dict?)")
     return x
+
+
+# ------------------------------------------------------------------------------------------------
+# Row f4 (next): voxel predictions -> mesh-vertex instance labels, literal restatement of the loops of
+# tools/scannet_benchmark/vox2mesh.py:55-106 (small cases only: it is voxel-by-voxel / vertex-by-vertex Python)
+# ------------------------------------------------------------------------------------------------
+def vox2mesh_paint(pred_box, pred_class, pred_conf, pred_mask, dims):
+    scene = np.zeros(dims)
+    for box_ind, box in enumerate(pred_box):  # vox2mesh.py:55-69
+        lo = [int(round(box[a])) for a in range(3)]
+        hi = [int(round(box[a + 3])) for a in range(3)]
+        for i in range(lo[0], hi[0]):
+            for j in range(lo[1], hi[1]):
+                for k in range(lo[2], hi[2]):
+                    if pred_mask[box_ind][i - lo[0], j - lo[1], k - lo[2]] != 0 and scene[i, j, k] == 0:
+                        scene[i, j, k] = box_ind * 100 + pred_class[box_ind] + pred_conf[box_ind] - 0.01
+    return scene
+
+
+def vox2mesh_labels(mesh_vertices, world2grid, scene):
+    """-> (instance_class, instance_mask, instance_conf) dicts as vox2mesh.py:83-106 builds them; vertices whose
+    3x3x3 neighbourhood leaves the volume are skipped (the reference would index out of range there)."""
+    def nn_search(x, y, z):  # vox2mesh.py:71-81
+        if scene[x, y, z] != 0:
+            return x, y, z
+        for i in [-1, 0, 1]:
+            for j in [-1, 0, 1]:
+                for k in [-1, 0, 1]:
+                    if scene[x + i, y + j, z + k] != 0:
+                        return x + i, y + j, z + k
+        return -1, -1, -1
+
+    instance_mask, instance_conf, instance_class = {}, {}, {}
+    for ind, vertex in enumerate(mesh_vertices):
+        g = np.round(np.matmul(world2grid, np.append(vertex, 1)))
+        x, y, z = int(round(g[0])), int(round(g[1])), int(round(g[2]))
+        if not (1 <= x <= scene.shape[0] - 2 and 1 <= y <= scene.shape[1] - 2 and 1 <= z <= scene.shape[2] - 2):
+            continue
+        x, y, z = nn_search(x, y, z)
+        if x == -1:
+            continue
+        conf = np.modf(scene[x, y, z])[0]
+        instance_id = int(int(scene[x, y, z]) / 100)
+        class_id = int(scene[x, y, z]) % 100
+        if instance_id not in instance_class:
+            instance_class[instance_id] = class_id
+            instance_mask[instance_id] = [ind]
+            instance_conf[instance_id] = conf
+        else:
+            instance_mask[instance_id].append(ind)
+    return instance_class, instance_mask, instance_conf
