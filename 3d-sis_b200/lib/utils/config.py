@@ -36,6 +36,8 @@ def _defaults():
              USE_IMAGES=False, ONLY_IMAGES=False, USE_IMAGES_GT=True, NUM_IMAGES=1, NUM_2D_CLASSES=41,
              PRETRAINED_ENET_PATH="", IMAGE_SHAPE=[328, 256], DEPTH_SHAPE=[41, 32], NUM_IMAGE_CHANNELS=128,
              PROJ_DEPTH_MIN=0.1, PROJ_DEPTH_MAX=4.0, TEST_SAVE_DIR="", LABEL_MAP="", MODE="",
+             BASE_IMAGE_PATH="", IMAGE_TYPE="color2", IMAGE_EXT=".jpg",  # frame folders (reference config.py:191-219)
+             COLOR_MEAN=[0.47083, 0.44685, 0.40733], COLOR_STD=[0.27861, 0.27409, 0.28844],
              INTRINSIC=[[35.5070229, 0, 20, 0], [0, 36.9504013, 15.5, 0], [0, 0, 1, 0], [0, 0, 0, 1]])
     # where anchor tables live; the reference opens 'experiments/anchors/<name>' relative to its cwd
     c.ANCHOR_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))),
