@@ -29,11 +29,17 @@ class _Conv(C.Structure):
 
 
 class EnetEncoder:
-    def __init__(self, params, device):
-        if not os.path.exists(_LIB):
-            raise ImportError(f"{_LIB} not found: build it with `make -C 3d-sis_b200/csrc/enet2d`")
-        self.lib = C.CDLL(_LIB)
+    def __init__(self, params, device, lib=None):
+        """lib: object with the four sis3d_enet_* entry points (default: libsis3d_enet.so).  tests/test_enet_executor.py
+        passes a numpy model of the C contract (sis3d_enet.h) with device='cpu' to check this executor's wiring without a GPU."""
         self.dev = torch.device(device)
+        if lib is None:
+            if self.dev.type != "cuda":
+                raise RuntimeError("libsis3d_enet.so operates on CUDA memory (no CPU fallback)")
+            if not os.path.exists(_LIB):
+                raise ImportError(f"{_LIB} not found: build it with `make -C 3d-sis_b200/csrc/enet2d`")
+            lib = C.CDLL(_LIB)
+        self.lib = lib
         self.ops = []
         stream = self._stream()
         for op in compile_enet([p.float().cpu() for p in params]):
@@ -54,11 +60,11 @@ class EnetEncoder:
                 self.ops.append(dict(kind="add", slope=op[3].contiguous().to(self.dev), cout=op[5]))
             elif op[0] == "pool":
                 self.ops.append(dict(kind="pool"))
-        torch.cuda.current_stream().synchronize()
+        if self.dev.type == "cuda":
+            torch.cuda.current_stream().synchronize()
 
-    @staticmethod
-    def _stream():
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream) if self.dev.type == "cuda" else None
 
     @staticmethod
     def _check(rc):
