@@ -6,7 +6,13 @@
 // A is gathered on the fly (zero outside the image == PyTorch zero padding), dilation and stride in the tap offsets;
 // B is the packed weight [K][ldw].  Register tile 4 x 4 per thread (256 threads: 16 x 16), BK = 16, next chunk's global
 // loads in flight while the current one is multiplied -- the structure of conv3d_igemm_f32 (conv_simt.cu).
+#ifdef SIS3D_HOST_EMU  // host emulation build (tests/test_enet_executor.py): same source, blocks run as std::threads
+#include "host_emu.h"
+#define SIS3D_LAUNCH(kernel, grid, block, stream, ...) emu_launch(kernel, grid, block, __VA_ARGS__)
+#else
 #include <cuda_runtime.h>
+#define SIS3D_LAUNCH(kernel, grid, block, stream, ...) kernel<<<grid, block, 0, (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#endif
 #include <math.h>
 #include <stdint.h>
 #include "sis3d_enet.h"
@@ -198,7 +204,7 @@ extern "C" int sis3d_enet_pack_weight(const float *w, int cout, int cin, int kh,
     const int ldw = (cout + 3) / 4 * 4;
     const int64_t total = (int64_t)kh * kw * cin * ldw;
     const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-    enet_pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, cout, cin, kh, kw, ldw, packed);
+    SIS3D_LAUNCH(enet_pack_weight_kernel, dim3(blocks), dim3(256), stream, w, cout, cin, kh, kw, ldw, packed);
     return done();
 }
 
@@ -212,7 +218,7 @@ extern "C" int sis3d_enet_conv2d(const sis3d_enet_conv *p, void *stream) {
     if (((uintptr_t)a.w) & 15) return -1;
     const int64_t m_total = (int64_t)a.N * a.Ho * a.Wo;
     dim3 grid((unsigned)((m_total + BM - 1) / BM), (unsigned)((a.cout + BN - 1) / BN));
-    enet_conv2d_kernel<<<grid, THREADS, 0, (cudaStream_t)stream>>>(a);
+    SIS3D_LAUNCH(enet_conv2d_kernel, grid, dim3(THREADS), stream, a);
     return done();
 }
 
@@ -222,14 +228,14 @@ extern "C" int sis3d_enet_pool_affine(const float *in, int64_t sn, int64_t sy, i
     if (!in || !scale || !shift || !slope || !out || N <= 0 || H < 2 || W < 2 || C <= 0 || out_ld < out_coff + C) return -1;
     const int64_t total = (int64_t)N * (H / 2) * (W / 2) * C;
     const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-    enet_pool_affine_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, sn, sy, sx, sc, N, H, W, C, scale, shift, slope, out, out_ld,
-                                                                     out_coff);
+    SIS3D_LAUNCH(enet_pool_affine_kernel, dim3(blocks), dim3(256), stream, in, sn, sy, sx, sc, N, H, W, C, scale, shift, slope, out, out_ld,
+                 out_coff);
     return done();
 }
 
 extern "C" int sis3d_enet_to_nchw(const float *in, int ld, int coff, int N, int64_t P, int C, float *out, void *stream) {
     if (!in || !out || N <= 0 || P <= 0 || C <= 0 || ld < coff + C) return -1;
     dim3 grid((unsigned)((P + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N);
-    enet_to_nchw_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(in, ld, coff, P, C, out);
+    SIS3D_LAUNCH(enet_to_nchw_kernel, grid, dim3(32, 8), stream, in, ld, coff, P, C, out);
     return done();
 }

@@ -85,3 +85,27 @@ def test_executor_wiring_reproduces_reference_features():
     ref = torch.from_numpy(g["features"])
     assert y.shape == ref.shape
     assert float((y - ref).abs().max()) < 2e-4 and float((y - ref).norm() / ref.norm()) < 2e-6
+
+
+def test_cuda_source_under_host_emulation_matches_the_contract_model():
+    """The SAME enet2d.cu that nvcc compiles for sm_100a, compiled for the host (csrc/enet2d/host_emu.h: one CUDA block =
+    blockDim std::threads meeting at a barrier for __syncthreads) and driven by the executor: checks the kernels' index
+    arithmetic, tap tables, shared-memory staging, epilogues and packing on a small image against the numpy contract model
+    and the torch program -- everything short of running on the GPU itself."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    from lib.nets import enet_program as E
+    d = os.path.join(ROOT, "3d-sis_b200", "csrc", "enet2d")
+    subprocess.check_call(["make", "-C", d, "emu"], stdout=subprocess.DEVNULL)
+    emu = C.CDLL(os.path.join(ROOT, "3d-sis_b200", "lib", "libsis3d_enet_emu.so"))
+    g = load_golden("enet_encoder.npz")
+    params = [torch.from_numpy(g[k]) for k in sorted(k for k in g if k.startswith("p"))]
+    x = torch.from_numpy(np.random.default_rng(5).standard_normal((2, 3, 48, 72)).astype(np.float32))
+    y_emu = EnetEncoder(params, "cpu", lib=emu)(x)
+    y_model = EnetEncoder(params, "cpu", lib=_NumpyEnetLib())(x)
+    with torch.no_grad():
+        y_ref = E.run_program(E.compile_enet(params), x)
+    assert y_emu.shape == y_ref.shape == (2, 128, 6, 9)
+    assert float((y_emu - y_model).abs().max()) < 1e-4
+    assert float((y_emu - y_ref).abs().max()) < 2e-4 and float((y_emu - y_ref).norm() / y_ref.norm()) < 1e-5
