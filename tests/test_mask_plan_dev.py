@@ -74,3 +74,36 @@ def test_device_planner_fixed_canvas_and_overflow(emu):
     assert p2.overflow == 1 and p2.n_kept == 8 and p2.n_tiles_tc == 0
     p3, _, _ = _run(emu, det, dims, 19, 64, 4)                          # more bricks than capacity
     assert p3.overflow == 1 and p3.n_tiles_tc == 0
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_shell_zero_makes_every_out_of_crop_neighbour_zero(emu, seed):
+    """Static-canvas companion kernel (csrc/wip/mask_shell_zero.cu) under host emulation: on a garbage-filled canvas every
+    voxel that a 3x3x3 tap of a crop voxel can touch outside its own crop reads zero afterwards; crop interiors are untouched."""
+    rng = np.random.default_rng(40 + seed)
+    nk = int(rng.integers(1, 9))
+    sizes = rng.integers(1, 9, (nk, 3)).astype(np.int32)
+    Yc, Zc = int(sizes[:, 1].max() + rng.integers(0, 3)), int(sizes[:, 2].max() + rng.integers(0, 3))
+    Xc = int((sizes[:, 0] + 1).sum())
+    row = 32  # bytes per voxel row in this test
+    canvas = np.full((Xc, Yc, Zc, row), 0xFF, dtype=np.uint8)
+    n_kept = np.array([nk], dtype=np.int32)
+    rc = emu.sis3d_mask_shell_zero(C.c_void_p(n_kept.ctypes.data), C.c_void_p(sizes.ctypes.data), 16, Xc, Yc, Zc, row,
+                                   C.c_void_p(canvas.ctypes.data), None)
+    assert rc == 0
+    zero = ~canvas.any(axis=3)
+    xoff = np.concatenate([[0], np.cumsum(sizes[:, 0] + 1)[:-1]])
+    inside = np.zeros((Xc, Yc, Zc), dtype=bool)
+    for j in range(nk):
+        w, h, l = sizes[j]
+        inside[xoff[j]:xoff[j] + w, :h, :l] = True
+    assert not (zero & inside).any(), "crop interiors must not be touched"
+    for j in range(nk):
+        w, h, l = (int(v) for v in sizes[j])
+        x0 = int(xoff[j])
+        lo = np.array([max(x0 - 1, 0), 0, 0])
+        hi = np.array([min(x0 + w + 1, Xc), min(h + 1, Yc), min(l + 1, Zc)])
+        halo = np.zeros((Xc, Yc, Zc), dtype=bool)
+        halo[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = True   # everything a tap of this crop can read inside the canvas
+        halo[x0:x0 + w, :h, :l] = False                       # minus the crop itself
+        assert zero[halo].all(), f"crop {j}: a readable out-of-crop voxel is not zero"
