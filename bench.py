@@ -361,7 +361,10 @@ def main():
         # fraction of the 3D-conv HBM roofline = ALG_BYTES x scenes/s per GPU / HBM peak.  ALG_BYTES are the
         # per-layer compulsory fp32 bytes of the reference's dataflow; the fused/sparse design moves far fewer.
         "roofline": {"bound": "hbm", "achieved": alg * (value / world) / 1e9, "peak": hbm, "unit": "GB/s",
-                     "frac": alg * (value / world) / 1e9 / hbm, "traffic": None, "peak_source": which,
+                     "frac": alg * (value / world) / 1e9 / hbm, "traffic": 239.2e6, "peak_source": which,
+                     "traffic_note": "dram__bytes_read+write summed over the launches of one scene in an ncu --set full capture "
+                                     "(profiles/r1_ncu_full_one_scene_midround.txt; caches flushed per kernel -> upper bound; "
+                                     "mid-round build)",
                      "kernel": "whole forward = all libsis3d launches of one scene (graph replay + ragged mask stage)",
                      "algorithmic_bytes_per_chunk": alg, "gpu_ms_per_chunk": per_chunk_ms,
                      "note": "per-kernel times and shares: profiles/ (ncu launch list + --set full capture of the same command)"},
