@@ -7,7 +7,7 @@
 // B is the packed weight [K][ldw].  Register tile 4 x 4 per thread (256 threads: 16 x 16), BK = 16, next chunk's global
 // loads in flight while the current one is multiplied -- the structure of conv3d_igemm_f32 (conv_simt.cu).
 #ifdef SIS3D_HOST_EMU  // host emulation build (tests/test_enet_executor.py): same source, blocks run as std::threads
-#include "host_emu.h"
+#include "../emu_shims/host_emu.h"
 #define SIS3D_LAUNCH(kernel, grid, block, stream, ...) emu_launch(kernel, grid, block, __VA_ARGS__)
 #else
 #include <cuda_runtime.h>

@@ -6,7 +6,7 @@
 // 0 = tight extents like the host planner.  Not compiled into libsis3d.so yet; not run on a GPU yet.  Its logic is
 // checked bit for bit against the host planner under host emulation (tests/test_mask_plan_dev.py).
 #ifdef SIS3D_HOST_EMU
-#include "../enet2d/host_emu.h"
+#include "../emu_shims/host_emu.h"
 #define SIS3D_LAUNCH(kernel, grid, block, stream, ...) emu_launch(kernel, grid, block, __VA_ARGS__)
 #else
 #include <cuda_runtime.h>

@@ -5,7 +5,7 @@
 // One CTA per (crop, face); element type is opaque (bytes per voxel row = row_bytes).  Checked under host emulation
 // against a brute-force "every out-of-crop neighbour of every crop voxel reads zero" test (tests/test_mask_plan_dev.py).
 #ifdef SIS3D_HOST_EMU
-#include "../enet2d/host_emu.h"
+#include "../emu_shims/host_emu.h"
 #define SIS3D_LAUNCH(kernel, grid, block, stream, ...) emu_launch(kernel, grid, block, __VA_ARGS__)
 #else
 #include <cuda_runtime.h>
