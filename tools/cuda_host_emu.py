@@ -53,9 +53,10 @@ def build(out, sources, tsan=False):
             files.append(dst)
         glue = os.path.join(tmp, "emu_glue.cpp")
         with open(glue, "w") as g:
-            g.write('#include "common.cuh"\nnamespace sis3d { unsigned long long g_launch_count = 0; }\n')
+            g.write('#include "common.cuh"\nnamespace sis3d { unsigned long long g_launch_count = 0; }\n'
+                    'extern "C" const char *sis3d_strerror(int code) { return code == 0 ? "ok" : "emulated libsis3d error"; }\n')
         cmd = ["g++", "-O1" if tsan else "-O2", "-g", "-std=c++20", "-DSIS3D_HOST_EMU", "-fPIC", "-shared", "-pthread",
-               "-Wno-unknown-pragmas", "-Wno-attributes", f"-I{os.path.join(CSRC, 'emu_shims')}", f"-I{CSRC}",
+               "-Wno-unknown-pragmas", "-Wno-attributes", "-ffp-contract=off", f"-I{os.path.join(CSRC, 'emu_shims')}", f"-I{CSRC}",
                f"-I{os.path.join(ROOT, 'include')}"] + (["-fsanitize=thread"] if tsan else []) + ["-o", out, glue] + files
         subprocess.check_call(cmd)
 
