@@ -8,8 +8,6 @@ typedef int cudaError_t;
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <class F> inline int cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 inline int cudaMemsetAsync(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
-// warp intrinsics are NOT modelled: kernels that use them must not be emulated (the shim only lets shared headers compile)
-template <class T> inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
 
 // ---- single-rounding float intrinsics (the emulation is compiled with -ffp-contract=off, so a*b and a+b round once each)
 #include <cmath>

@@ -1,0 +1,79 @@
+"""CPU: the SHIPPED projection and sparse back-projection kernels (csrc/project.cu with its warp scans / ballots,
+csrc/sparse.cu) compiled for the host (tools/cuda_host_emu.py, warp collectives modelled with per-warp barriers) and run
+through the same Python wrappers, against the oracle: index lists bit-exact, back-projected volume bit-exact, fused sparse
+back-projection + color.0 equal to the dense path."""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+import sis3d_synth as synth
+from lib.layer_utils import projection as P
+
+
+def _views(dims, n_img, seed):
+    data, boxes = synth.make_scene(seed, dims)
+    return synth.make_views(seed, dims, n_img, boxes)
+
+
+def _maps(oracle, dims, n_img, seed):
+    ocfg = oracle.make_cfg("scannet")
+    v = _views(dims, n_img, seed)
+    intr = ocfg.INTRINSIC
+    # per-view constants: the torch restatement (bit-identical to the native helper, tests/test_view_params.py)
+    vp = P._view_params_torch(intr, (41, 32), ocfg.PROJ_DEPTH_MIN, ocfg.PROJ_DEPTH_MAX, dims, torch.from_numpy(v["poses"]),
+                              torch.from_numpy(v["world2grid"]))
+    pix, counts = P.project_maps(vp, torch.from_numpy(v["depths"]).contiguous(), (intr[0][0], intr[1][1], intr[0][2], intr[1][2]),
+                                 (ocfg.PROJ_DEPTH_MIN, ocfg.PROJ_DEPTH_MAX, ocfg.VOXEL_SIZE), dims, 41, 32)
+    return ocfg, v, pix, counts
+
+
+def test_projection_index_lists_emulated_bit_exact(oracle, host_S):
+    S = host_S
+    dims, n_img = (36, 22, 32), 3
+    ocfg, v, pix, counts = _maps(oracle, dims, n_img, 202)
+    n0 = dims[0] * dims[1] * dims[2]
+    nbytes = int(S.lib.sis3d_project_compact_workspace_bytes(*dims))
+    covered = 0
+    for i in range(n_img):
+        m = oracle.compute_projection(ocfg, v["depths"][i], v["poses"][i], v["world2grid"], dims)
+        if m is None:
+            assert int(counts[i]) == 0
+            continue
+        l3w, l2w = (torch.as_tensor(t) for t in m)
+        assert int(counts[i]) == len(l3w)
+        lin3d, lin2d = torch.zeros(n0 + 1, dtype=torch.int64), torch.zeros(n0 + 1, dtype=torch.int64)
+        ws = torch.empty(max(nbytes, 8), dtype=torch.uint8)
+        S.check(S.lib.sis3d_project_compact(S.ptr(pix[i]), *dims, S.ptr(lin3d), S.ptr(lin2d), S.ptr(ws), C.c_size_t(nbytes), None))
+        k = int(lin3d[0])
+        assert k == len(l3w) and torch.equal(lin3d[1:k + 1], l3w) and torch.equal(lin2d[1:k + 1], l2w)
+        covered += k
+    assert covered > 300
+
+
+def test_backprojection_dense_and_sparse_fused_emulated(oracle, host_S):
+    S = host_S
+    dims, n_img, Cn, cout = (36, 22, 32), 3, 16, 32
+    ocfg, v, pix, counts = _maps(oracle, dims, n_img, 202)
+    feats = torch.from_numpy(v["feats"][:, :Cn]).contiguous()
+    pairs, n_pairs = torch.empty(3 * n_img, dtype=torch.int32), torch.empty(1, dtype=torch.int32)
+    S.check(S.lib.sis3d_backproject_pairs(S.ptr(counts), n_img, S.ptr(pairs), S.ptr(n_pairs), None))
+    vol = P.backproject(feats, pix, pairs, n_pairs, dims, 41, 32)          # dense: VC [X,Y,Z,C]
+    want, _ = oracle.backproject_views(ocfg, v["feats"][:, :Cn], v["depths"], v["poses"], v["world2grid"], dims)
+    assert torch.equal(vol.permute(3, 0, 1, 2), want[0])
+    assert 0 < float((vol != 0).float().mean()) < 0.2                      # the volume is sparse, as the design assumes
+    # fused sparse path (cover / gemm / combine) == relu(conv k2s2(dense volume))
+    w = torch.from_numpy((np.random.default_rng(1).standard_normal((cout, Cn, 2, 2, 2)) / np.sqrt(8 * Cn)).astype(np.float32))
+    packed = torch.empty(8 * Cn, cout)
+    S.check(S.lib.sis3d_pack_conv_weight(S.ptr(w), cout, Cn, 2, S.ptr(packed), None))
+    od = tuple(d // 2 for d in dims)
+    out = torch.empty(*od, cout)
+    feats_t = torch.empty(n_img, 41 * 32, Cn)
+    nbytes = int(S.lib.sis3d_backproject_conv_k2s2_workspace_bytes(*dims, cout))
+    ws = torch.empty(nbytes, dtype=torch.uint8)
+    S.check(S.lib.sis3d_backproject_conv_k2s2_ex(S.ptr(feats), S.ptr(feats_t), S.ptr(pix), S.ptr(pairs), S.ptr(n_pairs), n_img, Cn, 41,
+                                                 32, *dims, S.ptr(packed), cout, S.ptr(out), None, cout, 0, S.ptr(ws),
+                                                 C.c_size_t(nbytes), None))
+    ref = F.relu(F.conv3d(want, w, stride=2))[0].permute(1, 2, 3, 0)
+    torch.testing.assert_close(out, ref, atol=2e-5, rtol=1e-4)

@@ -19,24 +19,8 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 
 @pytest.fixture(scope="module")
-def emu(tmp_path_factory):
-    import cuda_host_emu
-    out = str(tmp_path_factory.mktemp("emu") / "librpn_emu.so")
-    cuda_host_emu.build(out, [os.path.join(ROOT, "3d-sis_b200", "csrc", f) for f in ("rpn.cu", "roi.cu")])
-    lib = C.CDLL(out)
-    for f in ("sis3d_nms_workspace_bytes", "sis3d_rpn_workspace_bytes"):
-        getattr(lib, f).restype = C.c_size_t
-    lib.sis3d_strerror.restype = C.c_char_p
-    return lib
-
-
-@pytest.fixture
-def host_S(monkeypatch, emu):
-    """Point the ctypes layer at the emulated library and let it accept host tensors."""
-    monkeypatch.setattr(S, "lib", emu)
-    monkeypatch.setattr(S, "ptr", lambda t: None if t is None else C.c_void_p(t.data_ptr()))
-    monkeypatch.setattr(S, "stream", lambda: None)
-    return S
+def emu(emu_lib):
+    return emu_lib
 
 
 def _p(t):

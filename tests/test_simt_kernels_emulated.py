@@ -18,11 +18,8 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 
 @pytest.fixture(scope="module")
-def emu(tmp_path_factory):
-    import cuda_host_emu
-    out = str(tmp_path_factory.mktemp("emu") / "libsimt_emu.so")
-    cuda_host_emu.build(out, [os.path.join(ROOT, "3d-sis_b200", "csrc", "conv_simt.cu")])
-    return C.CDLL(out)
+def emu(emu_lib):
+    return emu_lib
 
 
 def _p(t):

@@ -39,7 +39,7 @@ def rewrite(text):
         cfg = split_top(m.group(2))
         return f"emu_launch({m.group(1)}, dim3({cfg[0]}), dim3({cfg[1]}), "
     text = LAUNCH.sub(launch, text)
-    text = re.sub(r"extern\s+__shared__\s+([\w ]+?)\s+(\w+)\s*\[\s*\]\s*;", r"static \1 \2[1 << 16];", text)
+    text = re.sub(r"extern\s+__shared__\s+((?:__align__\(\d+\)\s+)?[\w ]+?)\s+(\w+)\s*\[\s*\]\s*;", r"static \1 \2[1 << 16];", text)
     return text
 
 
