@@ -119,18 +119,33 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// v = hi + lo with hi = tf32(v) (round to nearest, low 13 bits zero) and lo = tf32(v - hi) (v - hi is exact in fp32)
+__device__ __forceinline__ float tf32_rna_bits(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ void split_tf32(float v, float &hi, float &lo) {
+    hi = tf32_rna_bits(v);
+    lo = tf32_rna_bits(v - hi);
+}
+
 // stages: 4 for BN = 128 (128 KB), 3 for BN <= 64 so that three CTAs fit one SM (the grids of the narrow layers are
 // ~1.3-1.5 waves at two CTAs/SM)
 template <int BN>
 struct TcStages { static constexpr int value = BN >= 128 ? 4 : 3; };
 // stage count per kernel flavour: the 3x3x3 stages are 3x bigger (slab + three weight tiles)
-template <int BN, int KS, int ROWB>
-struct TcStagesOf { static constexpr int value = KS == 3 ? (BN >= 128 ? 3 : 2) : TcStages<BN>::value; };  // narrow 3x3x3 layers: 2 stages so 2-3 CTAs share an SM
-template <int BN, int KS, int ROWB, int BY, int N2 = 0>
+// X3 (error-compensated 3xTF32, 64-byte K rows): every stage also holds the low parts of A and B; BN = 32 keeps three
+// stages (96 KB, two CTAs per SM), BN = 64 two (88 KB, two CTAs per SM), BN = 128 three (204 KB)
+template <int BN, int KS, int ROWB, int X3 = 0>
+struct TcStagesOf {
+    static constexpr int value = KS == 3 ? (X3 ? (BN == 64 ? 2 : 3) : (BN >= 128 ? 3 : 2)) : TcStages<BN>::value;
+};  // narrow 3x3x3 layers: 2 stages so 2-3 CTAs share an SM
+template <int BN, int KS, int ROWB, int BY, int N2 = 0, int X3 = 0>
 constexpr size_t tc_smem_bytes() {
-    return (size_t)TcStagesOf<BN, KS, ROWB>::value *
+    return (size_t)TcStagesOf<BN, KS, ROWB, X3>::value * (1 + X3) *
                ((KS == 3 ? (16 / BY + 2) * BY * TC_BZ : TC_BM) * ROWB + (KS == 3 ? 3 : 1) * BN * ROWB) +
-           (size_t)N2 * 128 * (BN / 32) + 1024 + 256;
+           (size_t)(1 + X3) * N2 * 128 * (BN / 32) + 1024 + 256;
 }
 constexpr int tc_tmem_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
@@ -142,11 +157,21 @@ constexpr int tc_tmem_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 12
 // (aliasing the drained pipeline stages), multiplied by W3[N2][BN] (its own TMA tile, fetched at kernel start) into a second
 // TMEM accumulator, and only that N2-wide result -- plus residual and ReLU -- goes to global memory.  The BN-wide
 // intermediate never leaves the SM; operand values and summation order equal the two-kernel path bit for bit.
-template <int BN, int KS, int EB = 4, int ROWB = 128, int BY = 2, int N2 = 0>
+//
+// X3 = 1 (EB = 4 only): error-compensated 3xTF32.  Every fp32 operand is split as v = hi + lo with hi = tf32(v) (round to
+// nearest) and lo = tf32(v - hi); the product is accumulated as A_lo.B_hi + A_hi.B_lo + A_hi.B_hi in the same fp32 TMEM
+// accumulator (the dropped A_lo.B_lo term is ~2^-22 relative).  Weights are split once at pack time ([2][cout][K]: hi rows,
+// then lo rows); the activation slab is split IN SHARED MEMORY by warps 2-3 after the TMA lands (hi overwrites the slab, lo
+// goes to a second buffer of the same swizzled layout -- the split is elementwise, so the layout is untouched), published
+// to the MMA's async proxy with fence.proxy.async + the conv_done mbarrier.  No extra L2->SM traffic for activations; the
+// tensor pipe, which the narrow layers leave mostly idle, does 3x the MMAs.  Result: fp32-class accuracy (the integer
+// outputs of the detector -- top-N order, NMS keep lists, class argmax, crop bounds -- match the fp32 path) on tcgen05.
+template <int BN, int KS, int EB = 4, int ROWB = 128, int BY = 2, int N2 = 0, int X3 = 0>
 __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
                                                               const __grid_constant__ CUtensorMap tmB2, const TcArgs a) {
-    static_assert(N2 == 0 || (KS == 3 && EB == 4 && ROWB == 128), "conv3 fusion: TF32 3x3x3 kernels only");
+    static_assert(N2 == 0 || (KS == 3 && EB == 4), "conv3 fusion: TF32 3x3x3 kernels only");
+    static_assert(X3 == 0 || EB == 4, "3xTF32 splits fp32-stored operands");
     constexpr int KC = ROWB / EB;            // channels per pipeline stage
     constexpr int TC_BY = BY, TC_BX = 16 / BY;  // brick: BY = 2 -> 8x2x8 (whole volumes), BY = 4 -> 4x4x8 (small RoI crops)
     // 3x3x3: one stage = one (dy, dz) pair: an x-halo slab of (8+2) x-planes (160 rows) serves the three x-taps --
@@ -155,22 +180,25 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
     constexpr int A_ROWS = KS == 3 ? (TC_BX + 2) * TC_BY * TC_BZ : TC_BM;
     constexpr int A_BYTES = A_ROWS * ROWB;
     constexpr int B_BYTES = BN * ROWB;
-    constexpr int STAGE_BYTES = A_BYTES + XT * B_BYTES;
-    constexpr int TC_STAGES = TcStagesOf<BN, KS, ROWB>::value;
+    // stage layout: [A | A_lo (X3) | B x XT | B_lo x XT (X3)]
+    constexpr int B_OFF = (1 + X3) * A_BYTES;
+    constexpr int STAGE_BYTES = (1 + X3) * (A_BYTES + XT * B_BYTES);
+    constexpr int TC_STAGES = TcStagesOf<BN, KS, ROWB, X3>::value;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B needs 1024 B alignment
-    constexpr int B2_BYTES = N2 * 128 * (BN / 32);  // W3 as BN/32 K slices of [N2 rows][32 ch]
+    constexpr int B2_BYTES = (1 + X3) * N2 * 128 * (BN / 32);  // W3 as BN/32 K slices of [N2 rows][32 ch] (X3: hi slices, then lo)
     constexpr int TMEM_COLS = tc_tmem_cols(BN + N2);
     uint8_t *smem_b2 = smem + TC_STAGES * STAGE_BYTES;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_b2 + B2_BYTES);
     uint64_t *empty = full + TC_STAGES;
     uint64_t *acc_ready = empty + TC_STAGES;
     uint64_t *b2_full = acc_ready + 1, *acc2_ready = acc_ready + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_ready + 3);
+    uint64_t *conv_done = acc_ready + 3;  // X3: the converter warps finished splitting stage s
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(conv_done + TC_STAGES);
 
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); mbar_init(conv_done + i, 64); }
         mbar_init(acc_ready, 1);
         mbar_init(b2_full, 1);
         mbar_init(acc2_ready, 1);
@@ -213,33 +241,42 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
         if constexpr (N2 > 0) {
             mbar_expect_tx(b2_full, B2_BYTES);
 #pragma unroll
-            for (int kc = 0; kc < BN / 32; ++kc) tma_load_2d(smem_b2 + kc * N2 * 128, &tmB2, b2_full, kc * 32, 0);
+            for (int h = 0; h <= X3; ++h)  // X3: rows [N2, 2 N2) of the split W3 are the low parts
+#pragma unroll
+                for (int kc = 0; kc < BN / 32; ++kc)
+                    tma_load_2d(smem_b2 + (h * (BN / 32) + kc) * N2 * 128, &tmB2, b2_full, kc * 32, h * N2);
         }
         for (int it = 0; it < total; ++it) {
             const int s = it % TC_STAGES;
             const uint32_t ph = (it / TC_STAGES) & 1;
             mbar_wait(empty + s, ph ^ 1);
-            mbar_expect_tx(full + s, STAGE_BYTES);
+            mbar_expect_tx(full + s, STAGE_BYTES - X3 * A_BYTES);  // X3: A_lo is written by the converter warps, not by TMA
             const int tap = it / kchunks, kc = it - tap * kchunks;
             uint8_t *sa = smem + s * STAGE_BYTES;
             if constexpr (KS == 0) {
                 tma_load_2d(sa, &tmA, full + s, (chunk0 + it) * KC, x0);
-                tma_load_2d(sa + A_BYTES, &tmB, full + s, (chunk0 + it) * KC, n0);
+                tma_load_2d(sa + B_OFF, &tmB, full + s, (chunk0 + it) * KC, n0);
+                if constexpr (X3) tma_load_2d(sa + B_OFF + B_BYTES, &tmB, full + s, (chunk0 + it) * KC, a.cout + n0);
             } else if constexpr (KS == 1) {
                 tma_load_4d(sa, &tmA, full + s, kc * KC, z0, y0, x0);
-                tma_load_2d(sa + A_BYTES, &tmB, full + s, kc * KC, n0);
+                tma_load_2d(sa + B_OFF, &tmB, full + s, kc * KC, n0);
+                if constexpr (X3) tma_load_2d(sa + B_OFF + B_BYTES, &tmB, full + s, kc * KC, a.cout + n0);
             } else if constexpr (KS == 2) {
                 // 2x2x2 / stride 2: the tensor map traverses the input with element strides {1,2,2,2}, so the box that starts
                 // at input voxel (2 x0 + dx, 2 y0 + dy, 2 z0 + dz) lands as the 128 output rows of this brick for tap (dx,dy,dz)
                 const int dx = tap >> 2, dy = (tap >> 1) & 1, dz = tap & 1;
                 tma_load_4d(sa, &tmA, full + s, kc * KC, 2 * z0 + dz, 2 * y0 + dy, 2 * x0 + dx);
-                tma_load_2d(sa + A_BYTES, &tmB, full + s, tap * a.cin + kc * KC, n0);
+                tma_load_2d(sa + B_OFF, &tmB, full + s, tap * a.cin + kc * KC, n0);
+                if constexpr (X3) tma_load_2d(sa + B_OFF + B_BYTES, &tmB, full + s, tap * a.cin + kc * KC, a.cout + n0);
             } else {
                 const int dy = tap / 3, dz = tap % 3;  // tap = (dy, dz) pair; the slab covers x0-1 .. x0+8
                 tma_load_4d(sa, &tmA, full + s, kc * KC, z0 + dz - 1, y0 + dy - 1, x0 - 1);
 #pragma unroll
-                for (int dx = 0; dx < 3; ++dx)  // weight rows k = ((dx*3+dy)*3+dz)*C_in + c
-                    tma_load_2d(sa + A_BYTES + dx * B_BYTES, &tmB, full + s, ((dx * 3 + dy) * 3 + dz) * a.cin + kc * KC, n0);
+                for (int dx = 0; dx < 3; ++dx) {  // weight rows k = ((dx*3+dy)*3+dz)*C_in + c
+                    tma_load_2d(sa + B_OFF + dx * B_BYTES, &tmB, full + s, ((dx * 3 + dy) * 3 + dz) * a.cin + kc * KC, n0);
+                    if constexpr (X3)
+                        tma_load_2d(sa + B_OFF + (3 + dx) * B_BYTES, &tmB, full + s, ((dx * 3 + dy) * 3 + dz) * a.cin + kc * KC, a.cout + n0);
+                }
             }
         }
     } else if (threadIdx.x == 32) {
@@ -251,9 +288,9 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
         for (int it = 0; it < total; ++it) {
             const int s = it % TC_STAGES;
             const uint32_t ph = (it / TC_STAGES) & 1;
-            mbar_wait(full + s, ph);
+            mbar_wait(X3 ? conv_done + s : full + s, ph);  // X3: the split (which itself waited for the TMA) is done
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+            const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + B_OFF;
 #pragma unroll
             for (int dx = 0; dx < XT; ++dx) {
                 // x-tap dx: A rows start 16 rows (= two 8-row swizzle atoms) further into the slab
@@ -261,13 +298,38 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
 #pragma unroll
                 for (int k = 0; k < ROWB / 32; ++k) {  // one MMA consumes 32 B of K (8 tf32 / 16 f16): advance inside the swizzle atom
                     const uint32_t acc = (it | dx | k) ? 1u : 0u;
-                    if constexpr (EB == 4) umma_tf32(tmem_base, umma_desc<ROWB>(ax + k * 32), umma_desc<ROWB>(bx + k * 32), idesc, acc);
+                    if constexpr (X3) {  // small terms first: A_lo.B_hi + A_hi.B_lo + A_hi.B_hi
+                        const uint64_t ah = umma_desc<ROWB>(ax + k * 32), al = umma_desc<ROWB>(ax + A_BYTES + k * 32);
+                        const uint64_t bh = umma_desc<ROWB>(bx + k * 32), bl = umma_desc<ROWB>(bx + XT * B_BYTES + k * 32);
+                        umma_tf32(tmem_base, al, bh, idesc, acc);
+                        umma_tf32(tmem_base, ah, bl, idesc, 1u);
+                        umma_tf32(tmem_base, ah, bh, idesc, 1u);
+                    } else if constexpr (EB == 4) umma_tf32(tmem_base, umma_desc<ROWB>(ax + k * 32), umma_desc<ROWB>(bx + k * 32), idesc, acc);
                     else umma_f16(tmem_base, umma_desc<ROWB>(ax + k * 32), umma_desc<ROWB>(bx + k * 32), idesc, acc);
                 }
             }
             umma_commit(empty + s);  // frees the smem slot once these MMAs retire
         }
         umma_commit(acc_ready);
+    } else if (X3 && warp >= 2) {
+        // ===== operand splitter (warps 2-3): slab -> hi (in place) + lo (second buffer), same swizzled layout =====
+        const int t = threadIdx.x - 64;
+        for (int it = 0; it < total; ++it) {
+            const int s = it % TC_STAGES;
+            mbar_wait(full + s, (it / TC_STAGES) & 1);
+            float4 *hi = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES);
+            float4 *lo = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES + A_BYTES);
+#pragma unroll 2
+            for (int i = t; i < A_BYTES / 16; i += 64) {
+                const float4 v = hi[i];
+                float4 h, l;
+                split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+                hi[i] = h;
+                lo[i] = l;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA's async proxy
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(conv_done + s)) : "memory");
+        }
     }
     __syncwarp();
     if constexpr (KS == 0) {
@@ -302,6 +364,7 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
         // conv2's tile -> ReLU -> shared memory as the A operand of the 1x1 conv: row r, 16-byte chunk j of K slice kc at
         // kc*16 KB + r*128 + ((j ^ (r & 7)) << 4)  (the canonical SWIZZLE_128B K-major layout TMA would have produced)
         uint8_t *a2 = smem;  // aliases the pipeline stages: every TMA write landed and every MMA reading them retired
+        constexpr int A2_BYTES = (BN / 32) * (TC_BM * 128);  // X3: the low parts follow as a second tile of the same layout
 #pragma unroll 1
         for (int kc = 0; kc < BN / 32; ++kc) {
             float v[32];
@@ -314,8 +377,15 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
                     const float4 b = __ldg(reinterpret_cast<const float4 *>(a.bias_mid + kc * 32 + 4 * j));
                     o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                 }
-                *reinterpret_cast<float4 *>(row + ((j ^ (r & 7)) << 4)) =
-                    make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+                o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+                if constexpr (X3) {
+                    float4 h, l;
+                    split_tf32(o.x, h.x, l.x); split_tf32(o.y, h.y, l.y); split_tf32(o.z, h.z, l.z); split_tf32(o.w, h.w, l.w);
+                    *reinterpret_cast<float4 *>(row + ((j ^ (r & 7)) << 4)) = h;
+                    *reinterpret_cast<float4 *>(row + A2_BYTES + ((j ^ (r & 7)) << 4)) = l;
+                } else {
+                    *reinterpret_cast<float4 *>(row + ((j ^ (r & 7)) << 4)) = o;
+                }
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA's async proxy
@@ -330,9 +400,18 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
 #pragma unroll
             for (int kc = 0; kc < BN / 32; ++kc)
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_tf32(tmem_base + BN, umma_desc<128>(sa2 + kc * (TC_BM * 128) + k * 32),
-                              umma_desc<128>(sb2 + kc * (N2 * 128) + k * 32), idesc2, (kc | k) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t ah = umma_desc<128>(sa2 + kc * (TC_BM * 128) + k * 32), bh = umma_desc<128>(sb2 + kc * (N2 * 128) + k * 32);
+                    if constexpr (X3) {
+                        const uint64_t al = umma_desc<128>(sa2 + A2_BYTES + kc * (TC_BM * 128) + k * 32);
+                        const uint64_t bl = umma_desc<128>(sb2 + (BN / 32 + kc) * (N2 * 128) + k * 32);
+                        umma_tf32(tmem_base + BN, al, bh, idesc2, (kc | k) ? 1u : 0u);
+                        umma_tf32(tmem_base + BN, ah, bl, idesc2, 1u);
+                        umma_tf32(tmem_base + BN, ah, bh, idesc2, 1u);
+                    } else {
+                        umma_tf32(tmem_base + BN, ah, bh, idesc2, (kc | k) ? 1u : 0u);
+                    }
+                }
             umma_commit(acc2_ready);
         }
         __syncwarp();
@@ -402,6 +481,20 @@ __global__ void pack_conv_weight_tc_kernel(const float *w, int cout, int cin, in
     }
 }
 
+// 3xTF32 weights: rows [0, cout) = tf32(w) (round to nearest), rows [cout, 2 cout) = tf32(w - tf32(w)); same k order
+__global__ void pack_conv_weight_tc_x3_kernel(const float *w, int cout, int cin, int taps, float *out) {
+    const int64_t total = (int64_t)cout * taps * cin;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cin);
+        const int tap = (int)((i / cin) % taps);
+        const int n = (int)(i / ((int64_t)cin * taps));
+        float hi, lo;
+        split_tf32(w[((int64_t)n * cin + c) * taps + tap], hi, lo);
+        out[i] = hi;
+        out[total + i] = lo;
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -416,18 +509,18 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-template <int BN, int KS, int EB = 4, int ROWB = 128, int BY = 2, int N2 = 0>
+template <int BN, int KS, int EB = 4, int ROWB = 128, int BY = 2, int N2 = 0, int X3 = 0>
 static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcArgs &a, int n_tiles, cudaStream_t s,
-                     const CUtensorMap *tmB2 = nullptr) {
-    const size_t smem = tc_smem_bytes<BN, KS, ROWB, BY, N2>();
+                     const CUtensorMap *tmB2 = nullptr, int grid_z = 1) {
+    const size_t smem = tc_smem_bytes<BN, KS, ROWB, BY, N2, X3>();
     static bool attr_done = false;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(conv3d_k3_tc_kernel<BN, KS, EB, ROWB, BY, N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(conv3d_k3_tc_kernel<BN, KS, EB, ROWB, BY, N2, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return SIS3D_ELAUNCH;
         attr_done = true;
     }
-    dim3 grid(n_tiles, N2 > 0 ? 1 : a.cout / BN);
-    conv3d_k3_tc_kernel<BN, KS, EB, ROWB, BY, N2><<<grid, 128, smem, s>>>(tmA, tmB, tmB2 ? *tmB2 : tmB, a);
+    dim3 grid(n_tiles, N2 > 0 ? 1 : a.cout / BN, grid_z);
+    conv3d_k3_tc_kernel<BN, KS, EB, ROWB, BY, N2, X3><<<grid, 128, smem, s>>>(tmA, tmB, tmB2 ? *tmB2 : tmB, a);
     return finish_launch();
 }
 
@@ -471,11 +564,20 @@ extern "C" int sis3d_conv3d_k3_tc_supported(int cin, int cout) {
     return (cin % TC_KC == 0 && (cout == 32 || cout == 64 || cout % 128 == 0)) ? 1 : 0;
 }
 
-extern "C" int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const float *bias, const float *residual, int res_ld,
-                                  int res_coff, float *out, int out_ld, int out_coff, int X, int Y, int Z, int cin, int cout,
-                                  int ks, const int32_t *tiles, int n_tiles, int act, void *stream) {
+extern "C" int sis3d_pack_conv_weight_tc_x3(const float *w, int cout, int cin, int ks, float *w_x3, void *stream) {
+    if (!w || !w_x3 || cout <= 0 || cin <= 0 || (ks != 1 && ks != 2 && ks != 3)) return SIS3D_EINVAL;
+    const int taps = ks * ks * ks;
+    const int64_t total = (int64_t)cout * taps * cin;
+    pack_conv_weight_tc_x3_kernel<<<(int)imin64(cdiv64(total, 256), 148 * 8), 256, 0, (cudaStream_t)stream>>>(w, cout, cin, taps, w_x3);
+    return finish_launch();
+}
+
+static int conv3d_k3_tc_impl(const float *in, const float *w_tc, const float *bias, const float *residual, int res_ld,
+                             int res_coff, float *out, int out_ld, int out_coff, int X, int Y, int Z, int cin, int cout,
+                             int ks, const int32_t *tiles, int n_tiles, int act, void *stream, bool x3) {
     if (!in || !w_tc || !out || X <= 0 || Y <= 0 || Z <= 0 || (ks != 1 && ks != 2 && ks != 3)) return SIS3D_EINVAL;
     if (ks == 2 && (tiles || X < 2 || Y < 2 || Z < 2)) return SIS3D_EINVAL;
+    if (x3 && tiles) return SIS3D_EUNSUPPORTED;  // the ragged mask stage does not need the compensated product
     const int taps = ks * ks * ks;
     // explicit tile lists (ragged RoI crops) use 4x4x8 bricks, whole volumes 8x2x8 (sis3d_conv3d_tc_brick)
     const int by = (tiles && ks == 3 && cout == 64 && cin % 64 == 0) ? 4 : 2, bx = 16 / by;
@@ -485,6 +587,8 @@ extern "C" int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const floa
     EncodeTiledFn enc = get_encode();
     if (!enc) return SIS3D_EUNSUPPORTED;
     const int BN = cout >= 128 ? 128 : cout;
+    const int kc = x3 ? 16 : TC_KC;                   // x3: 64-byte K rows (SWIZZLE_64B) so hi + lo tiles fit the same smem
+    const CUtensorMapSwizzle sw = x3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
     const int sd = ks == 2 ? 2 : 1;                   // ks == 2 is the stride-2, pad-0 conv: X, Y, Z are the INPUT extents
     const int Xo = X / sd, Yo = Y / sd, Zo = Z / sd;  // output extents (floor, as nn.Conv3d)
     CUtensorMap tmA, tmB;
@@ -492,19 +596,19 @@ extern "C" int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const floa
         cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X};
         cuuint64_t strides[3] = {(cuuint64_t)cin * 4, (cuuint64_t)Z * cin * 4, (cuuint64_t)Y * Z * cin * 4};
         // with element strides the box is given in traversed elements: N loaded voxels = boxDim / stride
-        cuuint32_t box[4] = {TC_KC, (cuuint32_t)(TC_BZ * sd), (cuuint32_t)(by * sd), (cuuint32_t)((ks == 3 ? bx + 2 : bx) * sd)};
+        cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(TC_BZ * sd), (cuuint32_t)(by * sd), (cuuint32_t)((ks == 3 ? bx + 2 : bx) * sd)};
         cuuint32_t estr[4] = {1, (cuuint32_t)sd, (cuuint32_t)sd, (cuuint32_t)sd};
         if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return SIS3D_EINVAL;
     }
     {
-        cuuint64_t dims[2] = {(cuuint64_t)taps * cin, (cuuint64_t)cout};
+        cuuint64_t dims[2] = {(cuuint64_t)taps * cin, (cuuint64_t)cout * (x3 ? 2 : 1)};  // x3: hi rows, then lo rows
         cuuint64_t strides[1] = {(cuuint64_t)taps * cin * 4};
-        cuuint32_t box[2] = {TC_KC, (cuuint32_t)BN};
+        cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)BN};
         cuuint32_t estr[2] = {1, 1};
         if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)w_tc, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return SIS3D_EINVAL;
     }
     TcArgs a;
@@ -515,6 +619,27 @@ extern "C" int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const floa
     if (!tiles) n_tiles = cdiv(Xo, bx) * a.tiles_y * a.tiles_z;
     if (n_tiles <= 0) return SIS3D_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    if (x3) {
+        if (ks == 3) {
+            switch (BN) {
+                case 32: return launch_tc<32, 3, 4, 64, 2, 0, 1>(tmA, tmB, a, n_tiles, s);
+                case 64: return launch_tc<64, 3, 4, 64, 2, 0, 1>(tmA, tmB, a, n_tiles, s);
+                default: return launch_tc<128, 3, 4, 64, 2, 0, 1>(tmA, tmB, a, n_tiles, s);
+            }
+        }
+        if (ks == 2) {
+            switch (BN) {
+                case 32: return launch_tc<32, 2, 4, 64, 2, 0, 1>(tmA, tmB, a, n_tiles, s);
+                case 64: return launch_tc<64, 2, 4, 64, 2, 0, 1>(tmA, tmB, a, n_tiles, s);
+                default: return launch_tc<128, 2, 4, 64, 2, 0, 1>(tmA, tmB, a, n_tiles, s);
+            }
+        }
+        switch (BN) {
+            case 32: return launch_tc<32, 1, 4, 64, 2, 0, 1>(tmA, tmB, a, n_tiles, s);
+            case 64: return launch_tc<64, 1, 4, 64, 2, 0, 1>(tmA, tmB, a, n_tiles, s);
+            default: return launch_tc<128, 1, 4, 64, 2, 0, 1>(tmA, tmB, a, n_tiles, s);
+        }
+    }
     if (ks == 3) {
         if (by == 4) return launch_tc<64, 3, 4, 128, 4>(tmA, tmB, a, n_tiles, s);
         switch (BN) {
@@ -536,15 +661,28 @@ extern "C" int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const floa
         default: return launch_tc<128, 1>(tmA, tmB, a, n_tiles, s);
     }
 }
+extern "C" int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const float *bias, const float *residual, int res_ld,
+                                  int res_coff, float *out, int out_ld, int out_coff, int X, int Y, int Z, int cin, int cout,
+                                  int ks, const int32_t *tiles, int n_tiles, int act, void *stream) {
+    return conv3d_k3_tc_impl(in, w_tc, bias, residual, res_ld, res_coff, out, out_ld, out_coff, X, Y, Z, cin, cout, ks, tiles,
+                             n_tiles, act, stream, false);
+}
+// error-compensated 3xTF32 (fp32-class accuracy on the tensor cores): w_x3 from sis3d_pack_conv_weight_tc_x3
+extern "C" int sis3d_conv3d_k3_tc_x3(const float *in, const float *w_x3, const float *bias, const float *residual, int res_ld,
+                                     int res_coff, float *out, int out_ld, int out_coff, int X, int Y, int Z, int cin, int cout,
+                                     int ks, int act, void *stream) {
+    return conv3d_k3_tc_impl(in, w_x3, bias, residual, res_ld, res_coff, out, out_ld, out_coff, X, Y, Z, cin, cout, ks, nullptr, 0,
+                             act, stream, true);
+}
 
 // ---- bottleneck tail: 3x3x3 conv (cin -> cmid) + ReLU + 1x1 conv (cmid -> cout) + residual + act, one kernel ----------------
 extern "C" int sis3d_conv3d_k3_tc_fused_supported(int cin, int cmid, int cout) {
     return (cin % TC_KC == 0 && ((cmid == 32 && (cout == 32 || cout == 64)) || (cmid == 64 && cout == 128))) ? 1 : 0;
 }
-extern "C" int sis3d_conv3d_k3_tc_fused(const float *in, const float *w2_tc, const float *bias2, const float *w3_tc,
-                                        const float *bias3, const float *residual, int res_ld, int res_coff, float *out,
-                                        int out_ld, int out_coff, int X, int Y, int Z, int cin, int cmid, int cout, int act,
-                                        void *stream) {
+static int conv3d_k3_tc_fused_impl(const float *in, const float *w2_tc, const float *bias2, const float *w3_tc,
+                                   const float *bias3, const float *residual, int res_ld, int res_coff, float *out,
+                                   int out_ld, int out_coff, int X, int Y, int Z, int cin, int cmid, int cout, int act,
+                                   void *stream, bool x3) {
     if (!in || !w2_tc || !w3_tc || !out || X <= 0 || Y <= 0 || Z <= 0) return SIS3D_EINVAL;
     if (!sis3d_conv3d_k3_tc_fused_supported(cin, cmid, cout)) return SIS3D_EUNSUPPORTED;
     if (((uintptr_t)in | (uintptr_t)w2_tc | (uintptr_t)w3_tc | (uintptr_t)out) & 15) return SIS3D_EINVAL;
@@ -552,26 +690,29 @@ extern "C" int sis3d_conv3d_k3_tc_fused(const float *in, const float *w2_tc, con
     EncodeTiledFn enc = get_encode();
     if (!enc) return SIS3D_EUNSUPPORTED;
     const int by = 2, bx = 8;
+    const int kc = x3 ? 16 : TC_KC;
+    const CUtensorMapSwizzle sw = x3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const int halves = x3 ? 2 : 1;  // x3 weight tensors: hi rows, then lo rows
     CUtensorMap tmA, tmB, tmB2;
     cuuint32_t estr[4] = {1, 1, 1, 1};
     {
         cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X};
         cuuint64_t strides[3] = {(cuuint64_t)cin * 4, (cuuint64_t)Z * cin * 4, (cuuint64_t)Y * Z * cin * 4};
-        cuuint32_t box[4] = {TC_KC, TC_BZ, (cuuint32_t)by, (cuuint32_t)(bx + 2)};
+        cuuint32_t box[4] = {(cuuint32_t)kc, TC_BZ, (cuuint32_t)by, (cuuint32_t)(bx + 2)};
         if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return SIS3D_EINVAL;
     }
     {
-        cuuint64_t dims[2] = {(cuuint64_t)27 * cin, (cuuint64_t)cmid};
+        cuuint64_t dims[2] = {(cuuint64_t)27 * cin, (cuuint64_t)cmid * halves};
         cuuint64_t strides[1] = {(cuuint64_t)27 * cin * 4};
-        cuuint32_t box[2] = {TC_KC, (cuuint32_t)cmid};
+        cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)cmid};
         if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)w2_tc, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return SIS3D_EINVAL;
     }
     {
-        cuuint64_t dims[2] = {(cuuint64_t)cmid, (cuuint64_t)cout};
+        cuuint64_t dims[2] = {(cuuint64_t)cmid, (cuuint64_t)cout * halves};
         cuuint64_t strides[1] = {(cuuint64_t)cmid * 4};
         cuuint32_t box[2] = {TC_KC, (cuuint32_t)cout};
         if (enc(&tmB2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)w3_tc, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -580,38 +721,60 @@ extern "C" int sis3d_conv3d_k3_tc_fused(const float *in, const float *w2_tc, con
     }
     TcArgs a;
     a.bias = bias3; a.bias_mid = bias2; a.res = residual; a.out = out; a.tiles = nullptr; a.out16 = nullptr;
-    a.X = X; a.Y = Y; a.Z = Z; a.cin = cin; a.cout = cout; a.act = act;
+    // the main loop's weight rows (and their lo halves, x3) are indexed with the 3x3x3 conv's width, the epilogue with cout
+    a.X = X; a.Y = Y; a.Z = Z; a.cin = cin; a.cout = x3 ? cmid : cout; a.act = act;
     a.out_ld = out_ld; a.out_coff = out_coff; a.res_ld = res_ld; a.res_coff = res_coff;
     a.tiles_y = cdiv(Y, by); a.tiles_z = cdiv(Z, TC_BZ);
     a.gemm_m = 0; a.gemm_chunks_per_split = 0;
     const int n_tiles = cdiv(X, bx) * a.tiles_y * a.tiles_z;
     cudaStream_t s = (cudaStream_t)stream;
+    if (x3) {
+        if (cmid == 32 && cout == 32) return launch_tc<32, 3, 4, 64, 2, 32, 1>(tmA, tmB, a, n_tiles, s, &tmB2);
+        if (cmid == 32 && cout == 64) return launch_tc<32, 3, 4, 64, 2, 64, 1>(tmA, tmB, a, n_tiles, s, &tmB2);
+        return launch_tc<64, 3, 4, 64, 2, 128, 1>(tmA, tmB, a, n_tiles, s, &tmB2);
+    }
     if (cmid == 32 && cout == 32) return launch_tc<32, 3, 4, 128, 2, 32>(tmA, tmB, a, n_tiles, s, &tmB2);
     if (cmid == 32 && cout == 64) return launch_tc<32, 3, 4, 128, 2, 64>(tmA, tmB, a, n_tiles, s, &tmB2);
     return launch_tc<64, 3, 4, 128, 2, 128>(tmA, tmB, a, n_tiles, s, &tmB2);
 }
+extern "C" int sis3d_conv3d_k3_tc_fused(const float *in, const float *w2_tc, const float *bias2, const float *w3_tc,
+                                        const float *bias3, const float *residual, int res_ld, int res_coff, float *out,
+                                        int out_ld, int out_coff, int X, int Y, int Z, int cin, int cmid, int cout, int act,
+                                        void *stream) {
+    return conv3d_k3_tc_fused_impl(in, w2_tc, bias2, w3_tc, bias3, residual, res_ld, res_coff, out, out_ld, out_coff, X, Y, Z, cin,
+                                   cmid, cout, act, stream, false);
+}
+extern "C" int sis3d_conv3d_k3_tc_fused_x3(const float *in, const float *w2_x3, const float *bias2, const float *w3_x3,
+                                           const float *bias3, const float *residual, int res_ld, int res_coff, float *out,
+                                           int out_ld, int out_coff, int X, int Y, int Z, int cin, int cmid, int cout, int act,
+                                           void *stream) {
+    return conv3d_k3_tc_fused_impl(in, w2_x3, bias2, w3_x3, bias3, residual, res_ld, res_coff, out, out_ld, out_coff, X, Y, Z, cin,
+                                   cmid, cout, act, stream, true);
+}
 
 // ---- y[M][N] = act(x[M][K] . w[N][K]^T + b): fully connected layer on the tensor cores (TF32), split-K ------------
-static int gemm_tc_splits(int M, int N, int K) {
+static int gemm_tc_splits(int M, int N, int K, int kc) {
     const int tiles = cdiv(M, TC_BM) * (N / (N >= 128 ? 128 : N));
-    const int chunks = K / TC_KC;
-    int splits = max(1, min(chunks / 4, (kNumSMs + tiles - 1) / tiles));
+    const int chunks = K / kc;
+    int splits = max(1, min(chunks / (128 / kc), (kNumSMs + tiles - 1) / tiles));
     return splits;
 }
 extern "C" int sis3d_linear_tc_supported(int K, int N) { return (K % TC_KC == 0 && (N == 32 || N == 64 || N % 128 == 0)) ? 1 : 0; }
 extern "C" size_t sis3d_linear_tc_workspace_bytes(int M, int N, int K) {
-    return sizeof(float) * (size_t)gemm_tc_splits(M, N, K) * M * N + 16;
+    return sizeof(float) * (size_t)gemm_tc_splits(M, N, K, 16) * M * N + 16;  // the x3 variant splits K finer: covers both
 }
-extern "C" int sis3d_linear_tc(const float *x, const float *w_nk, const float *bias, float *y, int M, int K, int N, int act,
-                               void *workspace, size_t workspace_bytes, void *stream) {
+static int linear_tc_impl(const float *x, const float *w_nk, const float *bias, float *y, int M, int K, int N, int act,
+                          void *workspace, size_t workspace_bytes, void *stream, bool x3) {
     if (!x || !w_nk || !y || !workspace || M <= 0) return SIS3D_EINVAL;
     if (!sis3d_linear_tc_supported(K, N)) return SIS3D_EUNSUPPORTED;
     if (((uintptr_t)x | (uintptr_t)w_nk | (uintptr_t)workspace) & 15) return SIS3D_EINVAL;
     EncodeTiledFn enc = get_encode();
     if (!enc) return SIS3D_EUNSUPPORTED;
     const int BN = N >= 128 ? 128 : N;
-    int splits = gemm_tc_splits(M, N, K);
-    const int chunks = K / TC_KC;
+    const int kc = x3 ? 16 : TC_KC;
+    const CUtensorMapSwizzle sw = x3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    int splits = gemm_tc_splits(M, N, K, kc);
+    const int chunks = K / kc;
     const int per = cdiv(chunks, splits);
     splits = cdiv(chunks, per);
     if (workspace_bytes < sizeof(float) * (size_t)splits * M * N) return SIS3D_EWORKSPACE;
@@ -619,38 +782,43 @@ extern "C" int sis3d_linear_tc(const float *x, const float *w_nk, const float *b
     {
         cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
         cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-        cuuint32_t box[2] = {TC_KC, TC_BM};
+        cuuint32_t box[2] = {(cuuint32_t)kc, TC_BM};
         cuuint32_t estr[2] = {1, 1};
         if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return SIS3D_EINVAL;
-        cuuint64_t dimsb[2] = {(cuuint64_t)K, (cuuint64_t)N};
-        cuuint32_t boxb[2] = {TC_KC, (cuuint32_t)BN};
+        cuuint64_t dimsb[2] = {(cuuint64_t)K, (cuuint64_t)N * (x3 ? 2 : 1)};
+        cuuint32_t boxb[2] = {(cuuint32_t)kc, (cuuint32_t)BN};
         if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)w_nk, dimsb, strides, boxb, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return SIS3D_EINVAL;
     }
     TcArgs a = {};
     a.out = (float *)workspace; a.out_ld = N; a.cin = K; a.cout = N; a.gemm_m = M; a.gemm_chunks_per_split = per;
     cudaStream_t s = (cudaStream_t)stream;
-    dim3 grid(cdiv(M, TC_BM), N / BN, splits);
+    const int mt = cdiv(M, TC_BM);
     int rc;
-    if (BN == 32) {
-        const size_t smem = (size_t)TcStages<32>::value * (TC_A_BYTES + 32 * 128) + 1280;
-        cudaFuncSetAttribute(conv3d_k3_tc_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        conv3d_k3_tc_kernel<32, 0><<<grid, 128, smem, s>>>(tmA, tmB, tmB, a);
-    } else if (BN == 64) {
-        const size_t smem = (size_t)TcStages<64>::value * (TC_A_BYTES + 64 * 128) + 1280;
-        cudaFuncSetAttribute(conv3d_k3_tc_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        conv3d_k3_tc_kernel<64, 0><<<grid, 128, smem, s>>>(tmA, tmB, tmB, a);
+    if (x3) {
+        rc = BN == 32 ? launch_tc<32, 0, 4, 64, 2, 0, 1>(tmA, tmB, a, mt, s, nullptr, splits)
+           : BN == 64 ? launch_tc<64, 0, 4, 64, 2, 0, 1>(tmA, tmB, a, mt, s, nullptr, splits)
+                      : launch_tc<128, 0, 4, 64, 2, 0, 1>(tmA, tmB, a, mt, s, nullptr, splits);
     } else {
-        const size_t smem = (size_t)TcStages<128>::value * (TC_A_BYTES + 128 * 128) + 1280;
-        cudaFuncSetAttribute(conv3d_k3_tc_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        conv3d_k3_tc_kernel<128, 0><<<grid, 128, smem, s>>>(tmA, tmB, tmB, a);
+        rc = BN == 32 ? launch_tc<32, 0>(tmA, tmB, a, mt, s, nullptr, splits)
+           : BN == 64 ? launch_tc<64, 0>(tmA, tmB, a, mt, s, nullptr, splits)
+                      : launch_tc<128, 0>(tmA, tmB, a, mt, s, nullptr, splits);
     }
+    if (rc) return rc;
     gemm_splitk_reduce_kernel<<<cdiv(M * N, 256), 256, 0, s>>>((const float *)workspace, splits, (int64_t)M * N, bias, y, M, N, act);
-    rc = finish_launch(2);
-    return rc;
+    return finish_launch();
+}
+extern "C" int sis3d_linear_tc(const float *x, const float *w_nk, const float *bias, float *y, int M, int K, int N, int act,
+                               void *workspace, size_t workspace_bytes, void *stream) {
+    return linear_tc_impl(x, w_nk, bias, y, M, K, N, act, workspace, workspace_bytes, stream, false);
+}
+// w_x3 = sis3d_pack_conv_weight_tc_x3(w[N][K] viewed as a 1x1 conv): [2][N][K]
+extern "C" int sis3d_linear_tc_x3(const float *x, const float *w_x3, const float *bias, float *y, int M, int K, int N, int act,
+                                  void *workspace, size_t workspace_bytes, void *stream) {
+    return linear_tc_impl(x, w_x3, bias, y, M, K, N, act, workspace, workspace_bytes, stream, true);
 }
 
 // ---- fp16-operand variant (kind::f16): activations and weights stored as fp16, fp32 accumulation in TMEM ----------

@@ -69,7 +69,8 @@ SYMBOLS = ["sis3d_strerror", "sis3d_version", "sis3d_launch_count", "sis3d_nms_w
            "sis3d_backproject_conv_k2s2_ex", "sis3d_linear_workspace_bytes", "sis3d_linear", "sis3d_linear_tc_supported", "sis3d_linear_tc_workspace_bytes", "sis3d_linear_tc", "sis3d_mlp_tail", "sis3d_pack_conv_weight_tc", "sis3d_conv3d_k3_tc_supported", "sis3d_conv3d_tc_brick", "sis3d_conv3d_k3_tc",
            "sis3d_conv3d_k3_tc_fused_supported", "sis3d_conv3d_k3_tc_fused",
            "sis3d_rpn_workspace_bytes", "sis3d_rpn_proposals", "sis3d_detect_decode", "sis3d_mask_plan_build", "sis3d_mask_stage_launch", "sis3d_memcpy_async",
-           "sis3d_mask_select"]
+           "sis3d_mask_select", "sis3d_pack_conv_weight_tc_x3", "sis3d_conv3d_k3_tc_x3", "sis3d_conv3d_k3_tc_fused_x3",
+           "sis3d_linear_tc_x3"]
 
 lib.sis3d_strerror.restype = C.c_char_p
 lib.sis3d_launch_count.restype = C.c_int64

@@ -98,11 +98,11 @@ class Network(nn.Module):
         self._keep_debug = False
         self._packed_tc = {}
         self._packed_h = {}
-        # conv math: 'tf32' = tcgen05 with fp32-stored operands (default), 'fp16' = tcgen05 with fp16-stored operands
-        # (same 11-bit significand, half the L2 traffic), 'fp32' = CUDA-core exact path
-        # 'mixed' = TF32 operands in the static stage, fp16-stored operands in the ragged mask stage, which is bound by
-        # the L2->SM operand feed (profiles/): halving the operand bytes there is worth more than anywhere else
-        self.set_conv_math(os.environ.get("SIS3D_CONV_MATH", str(cfg.get("CONV_MATH", "mixed"))).lower())
+        self._packed_x3 = {}
+        # conv math (see set_conv_math).  Default 'exact': error-compensated 3xTF32 (fp32-class accuracy, tcgen05) in the
+        # static stage -- everything that decides an integer output: proposal order, NMS keep list, class argmax, crop
+        # bounds -- and fp16-stored operands in the ragged mask stage, whose outputs carry the 1e-3 tolerance.
+        self.set_conv_math(os.environ.get("SIS3D_CONV_MATH", str(cfg.get("CONV_MATH", "exact"))).lower())
         self._graphs = {}
         self._slots = []
         self._branches = os.environ.get("SIS3D_BRANCHES", "1") != "0"
@@ -129,6 +129,12 @@ class Network(nn.Module):
         self._pack_dirty = True
         self._arena = {}  # grow-only device/pinned workspaces for the ragged (per-scene sized) stage
         self._use_graph = os.environ.get("SIS3D_CUDA_GRAPH", "1") != "0"
+        # a shape is captured the SIS3D_GRAPH_AFTER-th time it is seen (whole-scene inference meets many one-off shapes: those
+        # run eagerly), and every stream slot keeps at most SIS3D_GRAPH_CACHE captured shapes (LRU; a graph owns its static
+        # buffers and a private memory pool, so an unbounded cache would grow until OOM)
+        self._graph_after = max(1, int(os.environ.get("SIS3D_GRAPH_AFTER", "2")))
+        self._graph_cache = max(1, int(os.environ.get("SIS3D_GRAPH_CACHE", "4")))
+        self._shape_seen = {}
         self._prof = None  # name -> [(start_event, end_event)] when per-kernel timing is on (bench.py)
 
     # ------------------------------------------------------------------ parameters
@@ -201,12 +207,22 @@ class Network(nn.Module):
     def _version(self):
         return tuple((n, p._version, p.data_ptr()) for n, p in self.named_parameters())
 
+    MATH_MODES = {  # mode -> (static-stage conv math, mask-stage conv math)
+        "exact": ("tf32x3", "fp16"),   # default: integer outputs equal the fp32 path, masks within 1e-3
+        "tf32x3": ("tf32x3", "tf32"),
+        "mixed": ("tf32", "fp16"),     # fastest; detections equal the reference only up to near-tied scores
+        "tf32": ("tf32", "tf32"),
+        "fp16": ("fp16", "fp16"),
+        "fp32": ("fp32", "fp32"),      # CUDA-core kernels throughout
+    }
+
     def set_conv_math(self, mode):
-        """'fp32' CUDA-core exact path | 'tf32' | 'fp16' | 'mixed' (TF32 static stage + fp16-operand mask stage)."""
-        if mode not in ("fp32", "tf32", "fp16", "mixed"):
-            raise S.Sis3dError(f"unknown conv math {mode!r} (fp32 | tf32 | fp16 | mixed)")
-        self.__dict__["_math"] = "tf32" if mode == "mixed" else mode
-        self.__dict__["_mask_math"] = "fp16" if mode == "mixed" else mode
+        """'exact' (3xTF32 static stage + fp16-operand mask stage) | 'tf32x3' | 'mixed' (TF32 + fp16) | 'tf32' | 'fp16' |
+        'fp32' (CUDA-core path)."""
+        if mode not in self.MATH_MODES:
+            raise S.Sis3dError(f"unknown conv math {mode!r} ({' | '.join(self.MATH_MODES)})")
+        self.__dict__["_math"], self.__dict__["_mask_math"] = self.MATH_MODES[mode]
+        self.__dict__["_math_mode"] = mode
 
     def _ensure_packed(self):
         d = self.__dict__
@@ -221,7 +237,7 @@ class Network(nn.Module):
         self._pack_dirty = False
         if v == self._packed_version:
             return
-        self._packed, self._packed_tc, self._packed_h = {}, {}, {}
+        self._packed, self._packed_tc, self._packed_h, self._packed_x3 = {}, {}, {}, {}
         params = dict(self.named_parameters())
         for name, p in params.items():
             if not name.endswith(".weight"):
@@ -240,10 +256,17 @@ class Network(nn.Module):
                 wtc = torch.empty(cout, ks ** 3 * cin, dtype=torch.float32, device=w.device)
                 S.check(S.lib.sis3d_pack_conv_weight_tc(S.ptr(w), cout, cin, ks, S.ptr(wtc), S.stream()), "pack_tc")
                 self._packed_tc[base] = wtc
+                wx3 = torch.empty(2 * cout, ks ** 3 * cin, dtype=torch.float32, device=w.device)
+                S.check(S.lib.sis3d_pack_conv_weight_tc_x3(S.ptr(w), cout, cin, ks, S.ptr(wx3), S.stream()), "pack_x3")
+                self._packed_x3[base] = wx3
                 if ks != 2 and (cin % 64 == 0 or cin == 32):
                     w16 = torch.empty(cout, ks ** 3 * cin, dtype=torch.float16, device=w.device)
                     S.check(S.lib.sis3d_pack_conv_weight_tc_f16(S.ptr(w), cout, cin, ks, S.ptr(w16), S.stream()), "pack_f16")
                     self._packed_h[base] = w16
+            elif p.dim() == 2 and cin >= 1024 and S.lib.sis3d_linear_tc_supported(cin, cout):
+                wx3 = torch.empty(2 * cout, cin, dtype=torch.float32, device=w.device)  # nn.Linear [N][K] = a 1x1 conv
+                S.check(S.lib.sis3d_pack_conv_weight_tc_x3(S.ptr(w), cout, cin, 1, S.ptr(wx3), S.stream()), "pack_x3")
+                self._packed_x3[base] = wx3
         for lvl in (1, 2, 3):  # both RPN heads of a level as ONE 1x1 conv: [2A | 6A] output channels, zero-padded to a
             # tensor-core friendly width (32/64/128k) so the merged head runs on the tcgen05 kernel as well
             c, b = f"rpn_cls_score_net_level{lvl}.0", f"rpn_bbox_pred_net_level{lvl}"
@@ -263,6 +286,9 @@ class Network(nn.Module):
                     wtc = torch.empty(cpad, cin, dtype=torch.float32, device=w.device)
                     S.check(S.lib.sis3d_pack_conv_weight_tc(S.ptr(wp), cpad, cin, 1, S.ptr(wtc), S.stream()), "pack_tc")
                     self._packed_tc[f"rpn_heads_level{lvl}"] = wtc
+                    wx3 = torch.empty(2 * cpad, cin, dtype=torch.float32, device=w.device)
+                    S.check(S.lib.sis3d_pack_conv_weight_tc_x3(S.ptr(wp), cpad, cin, 1, S.ptr(wx3), S.stream()), "pack_x3")
+                    self._packed_x3[f"rpn_heads_level{lvl}"] = wx3
                     w16 = torch.empty(cpad, cin, dtype=torch.float16, device=w.device)
                     S.check(S.lib.sis3d_pack_conv_weight_tc_f16(S.ptr(wp), cpad, cin, 1, S.ptr(w16), S.stream()), "pack_f16")
                     self._packed_h[f"rpn_heads_level{lvl}"] = w16
@@ -350,6 +376,13 @@ class Network(nn.Module):
             raise S.Sis3dError(f"{name}: this layer needs the fp32 activation but only the fp16 twin was produced")
         if out.t is None and h_ptr is None:
             out.t = torch.empty(*out_dims, cout, dtype=torch.float32, device=dev)
+        if self._math == "tf32x3" and tc_ok and name in self._packed_x3 and out.t is not None and h_ptr is None:
+            tok = self._rec(f"conv_tc_x3[{name}]")
+            S.check(S.lib.sis3d_conv3d_k3_tc_x3(S.ptr(x.t), S.ptr(self._packed_x3[name]), S.ptr(bias), *res_args,
+                                                S.ptr(out.t), out.ld, out.coff, *x.dims, cin, cout, ks, act, S.stream()),
+                    f"conv3d_k3_tc_x3[{name}]")
+            self._rec_end(tok)
+            return out
         if self._math in ("tf32", "fp16") and tc_ok and name in self._packed_tc and out.t is not None and h_ptr is None:
             tok = self._rec(f"conv_tc[{name}]")
             S.check(S.lib.sis3d_conv3d_k3_tc(S.ptr(x.t), S.ptr(self._packed_tc[name]), S.ptr(bias), *res_args,
@@ -376,6 +409,14 @@ class Network(nn.Module):
         packed, bias, cout, cin, _ = self._packed[name]
         M = x.shape[0]
         y = torch.empty(M, cout, dtype=torch.float32, device=x.device)
+        if self._math == "tf32x3" and name in self._packed_x3:
+            nbytes = int(S.lib.sis3d_linear_tc_workspace_bytes(M, cout, cin))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            tok = self._rec(f"linear_tc_x3[{name}]")
+            S.check(S.lib.sis3d_linear_tc_x3(S.ptr(x), S.ptr(self._packed_x3[name]), S.ptr(bias), S.ptr(y), M, cin, cout, act,
+                                             S.ptr(ws), C.c_size_t(nbytes), S.stream()), f"linear_tc_x3[{name}]")
+            self._rec_end(tok)
+            return y
         if self._math == "tf32" and cin >= 1024 and S.lib.sis3d_linear_tc_supported(cin, cout):
             w_nk = dict(self.named_parameters())[name + ".weight"].detach()  # nn.Linear layout [N][K] is already K-major
             nbytes = int(S.lib.sis3d_linear_tc_workspace_bytes(M, cout, cin))
@@ -399,17 +440,20 @@ class Network(nn.Module):
         is a dense tensor, for the next block's first conv)."""
         y = self._conv(x, name + ".conv1", act=1, want32=False, want16=True)
         n2, n3 = name + ".conv2", name + ".conv3"
-        if self._math == "tf32" and self._fuse_bneck and n2 in self._packed_tc and n3 in self._packed_tc and y.t is not None:
+        x3 = self._math == "tf32x3"
+        wt = self._packed_x3 if x3 else self._packed_tc
+        if self._math in ("tf32", "tf32x3") and self._fuse_bneck and n2 in wt and n3 in wt and y.t is not None:
             _, _, cmid, cin, _ = self._packed[n2]
             cout = self._packed[n3][2]
             if y.ld == y.C and y.coff == 0 and S.lib.sis3d_conv3d_k3_tc_fused_supported(cin, cmid, cout):
                 # conv2 + conv3 (+x, ReLU) in one tcgen05 kernel: the cmid-wide activation never leaves the SM
                 if out is None:
                     out = Act(torch.empty(*y.dims, cout, dtype=torch.float32, device=y.t.device), y.dims, cout)
-                tok = self._rec(f"conv_tc_fused[{name}]")
-                S.check(S.lib.sis3d_conv3d_k3_tc_fused(S.ptr(y.t), S.ptr(self._packed_tc[n2]), S.ptr(self._packed[n2][1]),
-                                                       S.ptr(self._packed_tc[n3]), S.ptr(self._packed[n3][1]), S.ptr(x.t), x.ld, x.coff, S.ptr(out.t), out.ld, out.coff, *y.dims, cin,
-                                                       cmid, cout, 1, S.stream()), f"conv3d_k3_tc_fused[{name}]")
+                tok = self._rec(f"conv_tc_fused{'_x3' if x3 else ''}[{name}]")
+                fn = S.lib.sis3d_conv3d_k3_tc_fused_x3 if x3 else S.lib.sis3d_conv3d_k3_tc_fused
+                S.check(fn(S.ptr(y.t), S.ptr(wt[n2]), S.ptr(self._packed[n2][1]),
+                           S.ptr(wt[n3]), S.ptr(self._packed[n3][1]), S.ptr(x.t), x.ld, x.coff, S.ptr(out.t), out.ld, out.coff, *y.dims, cin,
+                           cmid, cout, 1, S.stream()), f"conv3d_k3_tc_fused[{name}]")
                 self._rec_end(tok)
                 return out
         y = self._conv(y, n2, act=1, want32=False, want16=True)
@@ -641,7 +685,7 @@ class Network(nn.Module):
         dev = scene_ncdhw.device
         X, Y, Z = (int(v) for v in scene_ncdhw.shape[2:])
         ncls = self._packed["mask_backbone.geometry.10"][2]
-        use_tc = self._math in ("tf32", "fp16") and "mask_backbone.geometry.2" in self._packed_tc
+        use_tc = self._mask_math in ("tf32", "fp16") and "mask_backbone.geometry.2" in self._packed_tc
         det_host = np.ascontiguousarray(det_host[:n], dtype=np.float32)
         plan = S.MaskPlan()
         cap = self._arena["mask_tables_host"].numel() if "mask_tables_host" in self._arena else 1 << 18
@@ -749,7 +793,11 @@ class Network(nn.Module):
         """Static input buffers + captured graph of `_static_stage` for one input shape."""
         st = self._graphs.get(key)
         if st is not None:
+            if next(reversed(self._graphs)) != key:
+                self._graphs[key] = self._graphs.pop(key)  # most recently used last
             return st
+        while len(self._graphs) >= self._graph_cache:  # LRU eviction: drops the graph, its static buffers and its pool
+            self._graphs.pop(next(iter(self._graphs)))
         w, h = int(cfg.DEPTH_SHAPE[0]), int(cfg.DEPTH_SHAPE[1])
         st = dict(scene=torch.zeros(1, 2, *dims, dtype=torch.float32, device=dev))
         if cfg.USE_IMAGES:
@@ -810,8 +858,13 @@ class Network(nn.Module):
         if data.shape[0] != 1:
             raise S.Sis3dError("batch size 1 only (as the reference's RoI pooling / proposal layer)")
         dims = tuple(int(v) for v in data.shape[2:])
+        home = self.__dict__.get("_home_stream")  # set while the pipelined scene loop runs
         h = dict(slot=slot, dims=dims, id=blobs["id"][0] if "id" in blobs else None, scene_info=data.shape[2:], blobs=blobs,
-                 killing_inds=killing_inds, dev=dev)
+                 killing_inds=killing_inds, dev=dev, fresh=home is None)
+        if home is not None and slot["stream"] is not None:
+            # tensors yielded by the scene loop live in slot-owned buffers (result ring, arena): whatever the consumer queued
+            # on its own stream to read them (a clone, a D2H copy) must finish before this slot's stream overwrites them
+            slot["stream"].wait_stream(home)
         with torch.no_grad(), Network._UseSlot(self, slot):
             lists = cfg.USE_IMAGES and "proj_ind_3d" in blobs
             use_graph = self._use_graph and not (self._keep_debug or self._prof is not None or lists)
@@ -828,7 +881,12 @@ class Network(nn.Module):
             if use_graph:
                 nv = fused["feats"].shape[0] if fused else 0
                 fc = fused["feats"].shape[1] if fused else 0
-                st = self._graph_state((dims, nv, fc, self._math), dims, nv, fc, dev)
+                key = (dims, nv, fc, self._math)
+                seen = self._shape_seen[key] = self._shape_seen.get(key, 0) + 1
+                if seen < self._graph_after and key not in self._graphs:
+                    use_graph = h["use_graph"] = False  # first sight of this shape: run eagerly, capture when it comes back
+            if use_graph:
+                st = self._graph_state(key, dims, nv, fc, dev)
                 st["scene"].copy_(data, non_blocking=True)
                 if fused:
                     st["feats"].copy_(fused["feats"], non_blocking=True)
@@ -873,7 +931,15 @@ class Network(nn.Module):
                 # results must not alias the replay buffers: ONE copy of the packed result buffer into one of two
                 # slot-owned, pre-carved result buffers (valid until this slot has been reused twice)
                 ring = st.get("result_ring")
-                if ring is None:
+                if h["fresh"]:
+                    # reference-compatible forward(): the caller may keep _predictions across scenes (the reference returns
+                    # fresh tensors), so hand out a private copy of the packed results and of the scene
+                    pk = torch.empty_like(st["outs"]["pack"])
+                    outs, _ = self._carve(pk, int(cfg.TEST.RPN_POST_NMS_TOP_N), max(int(cfg.NUM_CLASSES), 1))
+                    outs["num"] = outs["num"][:1]
+                    outs["pack"] = pk
+                    ring = False
+                elif ring is None:
                     ring = st["result_ring"] = []
                     for _ in range(2):
                         pk = torch.empty_like(st["outs"]["pack"])
@@ -882,10 +948,11 @@ class Network(nn.Module):
                         o["pack"] = pk
                         ring.append(o)
                     st["ring_pos"] = 0
-                outs = ring[st["ring_pos"]]
-                st["ring_pos"] ^= 1
+                if ring is not False:
+                    outs = ring[st["ring_pos"]]
+                    st["ring_pos"] ^= 1
                 outs["pack"].copy_(st["outs"]["pack"], non_blocking=True)
-                scene_t = st["scene"]
+                scene_t = st["scene"].clone() if h["fresh"] else st["scene"]
             else:
                 scene_t = data.to(dev, torch.float32, non_blocking=True).contiguous()
                 if fused:

@@ -226,3 +226,58 @@ def make_nms_boxes(seed, n=400, dims=(96, 48, 96), dup_frac=0.05):
         dst = rng.integers(0, n, ndup)
         boxes[dst] = boxes[src]
     return boxes.astype(np.float32)
+
+
+# ---------------------------------------------------------------- named cases shared by the parity tests, smoke() and bench.py
+CASES = {
+    "cfg1_32": dict(cfgname="scannet", dims=(32, 32, 32), n_img=0, seed=101, use_images=False, use_mask=False),
+    "odd_45x27x41": dict(cfgname="scannet", dims=(45, 27, 41), n_img=3, seed=202, use_images=True, use_mask=True),
+    "cfg2_96x48x96": dict(cfgname="scannet", dims=(96, 48, 96), n_img=5, seed=303, use_images=True, use_mask=True),
+    "suncg_40x24x40": dict(cfgname="suncg", dims=(40, 24, 40), n_img=3, seed=404, use_images=True, use_mask=True),
+}
+
+
+def build_case(port, c):
+    """(oracle cfg, weights, data, views) of a named case; `port` is the CPU checker module (oracle/port.py), passed in by
+    the test / bench leg that is allowed to use it."""
+    cfg = port.make_cfg(c["cfgname"], USE_IMAGES=c["use_images"], USE_MASK=c["use_mask"])
+    w = make_weights(seed=0, net=cfg.NET, use_images=c["use_images"], num_classes=cfg.NUM_CLASSES,
+                     a1=cfg.NUM_ANCHORS_LEVEL1, a2=cfg.NUM_ANCHORS_LEVEL2, use_mask=c["use_mask"])
+    data, boxes = make_scene(c["seed"], c["dims"])
+    views = None
+    if c["use_images"]:
+        views = make_views(c["seed"], c["dims"], c["n_img"], boxes, intrinsic=np.array(cfg.INTRINSIC, dtype=np.float32))
+    return cfg, w, data, views
+
+
+def make_net(c, keep_debug=True, math="fp32", weights=None):
+    """The product Network for a case: released yml config, seeded synthetic weights loaded through load_state_dict."""
+    import os
+    import torch
+    from lib.utils.config import cfg, cfg_from_file, cfg_reset
+    cfg_reset()
+    yml = "SUNCG" if c["cfgname"] == "suncg" else "ScanNet"
+    cfg_from_file(os.path.join(os.path.dirname(os.path.abspath(__file__)), "experiments", "cfgs", yml, "rpn_class_mask_5.yml"))
+    cfg.NUM_CLASSES = 26 if c["cfgname"] == "suncg" else 19
+    cfg.USE_IMAGES, cfg.USE_MASK, cfg.USE_IMAGES_GT = c["use_images"], c["use_mask"], True
+    from lib.nets import backbones
+    net = getattr(backbones, cfg.NET)()
+    net.init_modules()
+    w = weights if weights is not None else make_weights(
+        seed=0, net=cfg.NET, use_images=c["use_images"], num_classes=cfg.NUM_CLASSES, a1=cfg.NUM_ANCHORS_LEVEL1,
+        a2=cfg.NUM_ANCHORS_LEVEL2, use_mask=c["use_mask"])
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)
+    net._keep_debug = keep_debug
+    net.set_conv_math(math)
+    return net, cfg
+
+
+def make_blobs(c, data, views, pin=False):
+    """The reference's blob dict (lib/datasets/dataloader.py collate_fn) for one synthetic scene."""
+    import torch
+    t = (lambda a: torch.from_numpy(a).pin_memory()) if pin else torch.from_numpy
+    blobs = {"data": t(data), "id": ["synthetic"], "gt_box": [torch.zeros(0, 7)], "gt_mask": [[]]}
+    if views is not None:
+        blobs["nearest_images"] = {"images": [t(views["feats"])], "depths": [t(views["depths"])],
+                                   "poses": [t(views["poses"])], "world2grid": [t(views["world2grid"])]}
+    return blobs

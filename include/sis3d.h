@@ -189,6 +189,27 @@ int sis3d_conv3d_k3_tc_fused(const float *in, const float *w2_tc, const float *b
                              int Y, int Z, int cin, int cmid, int cout, int act, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Error-compensated 3xTF32 on the tensor cores ("x3"): same call sites and arguments as sis3d_conv3d_k3_tc /
+ * _fused / sis3d_linear_tc, fp32-class accuracy.  Every fp32 operand is split v = hi + lo (hi = tf32(v), round to
+ * nearest; lo = tf32(v - hi)) and the product accumulated as A_lo.B_hi + A_hi.B_lo + A_hi.B_hi in the fp32 TMEM
+ * accumulator.  Weights are split once (sis3d_pack_conv_weight_tc_x3 -> [2][cout][ks^3*cin]: hi rows, then lo rows; a
+ * [N][K] nn.Linear weight is packed as a ks = 1 conv); activations are split in shared memory after the TMA load, so
+ * they cross L2->SM once.  This is the mode in which the detector's integer outputs (top-N order, NMS keep lists, class
+ * argmax, crop bounds) match the fp32 reference (lib/layer_utils/proposal_layer.py:181-197, lib/nets/network.py:296-301)
+ * while the convolutions still run on tcgen05.  Whole volumes only (tiles = NULL).
+ * ---------------------------------------------------------------------------------------------- */
+int sis3d_pack_conv_weight_tc_x3(const float *w_oidhw, int cout, int cin, int ks, float *w_x3, void *stream);
+int sis3d_conv3d_k3_tc_x3(const float *in, const float *w_x3, const float *bias, const float *residual,
+                          int res_ld, int res_coff, float *out, int out_ld, int out_coff, int X, int Y,
+                          int Z, int cin, int cout, int ks, int act, void *stream);
+int sis3d_conv3d_k3_tc_fused_x3(const float *in, const float *w2_x3, const float *bias2, const float *w3_x3,
+                                const float *bias3, const float *residual, int res_ld, int res_coff, float *out,
+                                int out_ld, int out_coff, int X, int Y, int Z, int cin, int cmid, int cout, int act,
+                                void *stream);
+int sis3d_linear_tc_x3(const float *x, const float *w_x3, const float *bias, float *y, int M, int K, int N, int act,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * fp16-operand tensor-core path (tcgen05 kind::f16, fp32 accumulate): activations and weights are STORED as fp16 (same
  * 11-bit significand TF32 keeps, half the bytes through L2 -- the kernel is bound by operand feed).  in16 is a dense VC
  * fp16 tensor; w16 from sis3d_pack_conv_weight_tc_f16; outputs: out32 (fp32, may be NULL) and/or out16 (fp16 twin with

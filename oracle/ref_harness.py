@@ -168,3 +168,26 @@ def build_net(cfg, weights):
     missing = net.load_state_dict(sd, strict=True)
     net.eval()
     return net
+
+
+def reference_forward(net, cfg, data, views):
+    """One scene through the UNMODIFIED reference exactly as its driver does it (lib/model/trainval.py:797-822 with the
+    MAX_VOLUME=0 'CPU path' semantics): per-view ProjectionHelper.compute_projection, killing_inds for views without a valid
+    projection, index lists stacked densely, then Network.forward(blobs, 'TEST', killing_inds).  Returns net._predictions."""
+    from lib.layer_utils.projection import ProjectionHelper
+    blobs = {"data": torch.from_numpy(np.ascontiguousarray(data)), "id": ["synthetic"], "gt_box": [torch.zeros(0, 7)],
+             "gt_mask": [[]]}
+    killing = None
+    if views is not None:
+        helper = ProjectionHelper(cfg.INTRINSIC, cfg.PROJ_DEPTH_MIN, cfg.PROJ_DEPTH_MAX, cfg.DEPTH_SHAPE,
+                                  blobs["data"].shape[-3:], cfg.VOXEL_SIZE)
+        w2g = torch.from_numpy(views["world2grid"])
+        maps = [helper.compute_projection(torch.from_numpy(d), torch.from_numpy(c), w2g)
+                for d, c in zip(views["depths"], views["poses"])]
+        killing = [i for i, m in enumerate(maps) if m is None]
+        real = [m for m in maps if m is not None]
+        blobs["proj_ind_3d"] = [torch.stack([m[0] for m in real])]
+        blobs["proj_ind_2d"] = [torch.stack([m[1] for m in real])]
+        blobs["nearest_images"] = {"images": [torch.from_numpy(views["feats"])]}
+    net.forward(blobs, "TEST", killing)
+    return net._predictions

@@ -7,24 +7,7 @@ import torch
 import sis3d_synth as synth
 from conftest import load_golden
 
-CASES = {
-    "cfg1_32": dict(cfgname="scannet", dims=(32, 32, 32), n_img=0, seed=101, use_images=False, use_mask=False),
-    "odd_45x27x41": dict(cfgname="scannet", dims=(45, 27, 41), n_img=3, seed=202, use_images=True, use_mask=True),
-    "cfg2_96x48x96": dict(cfgname="scannet", dims=(96, 48, 96), n_img=5, seed=303, use_images=True, use_mask=True),
-    "suncg_40x24x40": dict(cfgname="suncg", dims=(40, 24, 40), n_img=3, seed=404, use_images=True, use_mask=True),
-}
-
-
-def build_case(port, c):
-    cfg = port.make_cfg(c["cfgname"], USE_IMAGES=c["use_images"], USE_MASK=c["use_mask"])
-    w = synth.make_weights(seed=0, net=cfg.NET, use_images=c["use_images"], num_classes=cfg.NUM_CLASSES,
-                           a1=cfg.NUM_ANCHORS_LEVEL1, a2=cfg.NUM_ANCHORS_LEVEL2, use_mask=c["use_mask"])
-    data, boxes = synth.make_scene(c["seed"], c["dims"])
-    views = None
-    if c["use_images"]:
-        views = synth.make_views(c["seed"], c["dims"], c["n_img"], boxes,
-                                 intrinsic=np.array(cfg.INTRINSIC, dtype=np.float32))
-    return cfg, w, data, views
+from sis3d_synth import CASES, build_case  # noqa: E402,F401  (shared with smoke() and bench.py)
 
 
 def sub(t, step):

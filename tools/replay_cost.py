@@ -6,8 +6,8 @@ for p in (os.path.join(ROOT, "3d-sis_b200"), ROOT, os.path.join(ROOT, "tests")):
 import numpy as np, torch
 torch.set_num_threads(1)
 import bench
-from test_gpu_forward import make_net
-from test_oracle_golden import CASES
+from sis3d_synth import make_net
+from sis3d_synth import CASES
 dev = torch.device("cuda", 0)
 net, cfg = make_net(CASES["cfg2_96x48x96"], keep_debug=False, math=os.environ.get("SIS3D_CONV_MATH", "mixed"))
 data, views = bench.case(1000)

@@ -8,8 +8,8 @@ if os.environ.get("SIS3D_HOST_THREADS"):
     torch.set_num_threads(int(os.environ["SIS3D_HOST_THREADS"]))
 print("torch threads", torch.get_num_threads(), "cpu_count", os.cpu_count(), "affinity", len(os.sched_getaffinity(0)))
 import bench
-from test_gpu_forward import make_net
-from test_oracle_golden import CASES
+from sis3d_synth import make_net
+from sis3d_synth import CASES
 
 dev = torch.device("cuda", 0)
 net, cfg = make_net(CASES["cfg2_96x48x96"], keep_debug=False, math=os.environ.get("SIS3D_CONV_MATH", "mixed"))

@@ -6,8 +6,8 @@ for p in (os.path.join(ROOT, "3d-sis_b200"), ROOT, os.path.join(ROOT, "tests")):
 import torch
 torch.set_num_threads(1)
 import bench
-from test_gpu_forward import make_net
-from test_oracle_golden import CASES
+from sis3d_synth import make_net
+from sis3d_synth import CASES
 from torch.profiler import profile, ProfilerActivity
 
 dev = torch.device("cuda", 0)
