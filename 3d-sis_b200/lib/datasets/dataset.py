@@ -16,16 +16,41 @@ from lib.datasets.scene_io import encode_tsdf, read_scene
 from lib.utils.config import cfg
 
 
+def load_mapping(label_file):
+    """nyu40 label csv -> (raw id -> consecutive id, class weights with the background weight first) (dataset.py:268-283)."""
+    import csv
+    mapping, pre = {}, {}
+    with open(label_file) as f:
+        for row in csv.DictReader(f, delimiter=","):
+            mapping[int(row["nyu40id"])] = int(row["mappedIdConsecutive"])
+            pre[int(row["mappedIdConsecutive"])] = float(row["weight"])
+    return mapping, [0.3280746813009404] + [pre[k] for k in sorted(pre)]
+
+
+def part_in_chunk(b):
+    """Fraction of a box inside the 96x48x96 chunk volume (dataset.py:219-229: the stored value is recomputed in chunk mode)."""
+    overall = (b[3] - b[0]) * (b[4] - b[1]) * (b[5] - b[2])
+    lo = [min(max(b[0], 0), 96), min(max(b[1], 0), 48), min(max(b[2], 0), 96)]
+    hi = [min(max(b[3], 0), 96), min(max(b[4], 0), 48), min(max(b[5], 0), 96)]
+    return (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]) / overall
+
+
 class Dataset(torch.utils.data.Dataset):
-    def __init__(self, data_location, mode="test", view_provider=None, label_mapping=None):
+    def __init__(self, data_location, mode="test", view_provider=None, label_mapping=None, label_weights=None):
         if isinstance(data_location, (list, tuple)):
             self.scenes = list(data_location)
+        elif os.path.isdir(data_location):
+            self.scenes = [os.path.join(data_location, x) for x in os.listdir(data_location)
+                           if os.path.isfile(os.path.join(data_location, x))]
         else:
             with open(data_location) as f:
                 self.scenes = [ln.strip() for ln in f if ln.strip()]
         self.mode = mode
         self.view_provider = view_provider
-        self.mapping = label_mapping
+        self.mapping, self.weights = label_mapping, label_weights
+        lm = str(cfg.get("LABEL_MAP", "") or "")
+        if self.mapping is None and lm and os.path.isfile(lm):  # the reference always loads cfg.LABEL_MAP (dataset.py:39-40)
+            self.mapping, self.weights = load_mapping(lm)
 
     def __len__(self):
         return len(self.scenes)
@@ -38,12 +63,21 @@ class Dataset(torch.utils.data.Dataset):
         gt_box[:, 0:3] = np.floor(gt_box[:, 0:3])
         gt_box[:, 3:6] = np.ceil(gt_box[:, 3:6])
         if self.mapping is not None:
-            gt_box[:, 6] = [self.mapping.get(int(v), 0) for v in gt_box[:, 6]]
+            gt_box[:, 6] = [self.mapping[int(v)] for v in gt_box[:, 6]]  # unknown raw labels raise, as in the reference
         masks = []
         for _, m in s["masks"]:
             m = m.astype(np.uint8)
             m[m > 1] = 0
             masks.append(m)
+        if (cfg.get("KEEP_THRESH", 0.0) or cfg.USE_IMAGES) and s["part_in_volume"] is not None:
+            # box filter (dataset.py:106-130): fraction inside the volume >= KEEP_THRESH and a non-zero class weight
+            stats = [part_in_chunk(gt_box[i]) if self.mode == "chunk" else float(s["part_in_volume"][i])
+                     for i in range(len(s["part_in_volume"]))]
+            kept = [i for i in range(len(stats)) if stats[i] >= float(cfg.get("KEEP_THRESH", 0.0))
+                    and (self.weights is None or self.weights[int(gt_box[i, 6])] != 0)]
+            gt_box = gt_box[kept] if kept else np.zeros((0, 7), np.float32)
+            if cfg.USE_MASK:
+                masks = [masks[i] for i in kept]
         max_h = 480 if self.mode == "benchmark" else 48  # dataset.py:192-205
         keep = [i for i, b in enumerate(gt_box) if b[1] <= max_h and b[4] <= max_h]
         gt_box = gt_box[keep] if len(keep) else np.zeros((0, 7), np.float32)

@@ -1,22 +1,20 @@
-"""ENet encoder executor over libsis3d_enet.so -- WORK IN PROGRESS for SURVEY row f2 (reference: lib/nets/enet.py:130-590,
-create_enet_for_3d :697-715; network.py:199-213 is where the features enter the 3-D network).
+"""ENet encoder executor over the sis3d_enet_* entry points of libsis3d.so (reference: lib/nets/enet.py:130-590,
+create_enet_for_3d :697-715; lib/nets/network.py:199-213 is where the features enter the 3-D network).
 
-NOT on the round-1 product path and not yet run on a GPU: `lib.nets.network` does not import this module, no parity claim
-is made.  The host side it builds on (lib/nets/enet_program.py: BatchNorm folding into a flat conv program) IS checked on
-the CPU against the unmodified reference.  tools/enet_check.py runs this executor against tests/golden/enet_encoder.npz.
+`Network` builds one when cfg.USE_IMAGES and not cfg.USE_IMAGES_GT, from the `image_enet_fixed.*` / `image_enet_trainable.*`
+entries of its state_dict (same names as the reference), so raw images [n,3,256,328] are a valid input of the hot path.  The
+host side (lib/nets/enet_program.py: BatchNorm folding into a flat conv program) is checked on the CPU against the unmodified
+reference; the kernels against tests/golden/enet_encoder.npz on the GPU (tests/test_gpu_enet.py).
 
 Every bottleneck is three (asymmetric: four) launches of one fp32 implicit-GEMM kernel with bias / residual / PReLU fused in
 the epilogue; the down-sampling skip (2x2 max-pool + zero channel padding) is read inside the last conv's epilogue."""
 from __future__ import annotations
 
 import ctypes as C
-import os
 
 import torch
 
 from lib.nets.enet_program import compile_enet
-
-_LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "libsis3d_enet.so")
 
 
 class _Conv(C.Structure):
@@ -30,15 +28,15 @@ class _Conv(C.Structure):
 
 class EnetEncoder:
     def __init__(self, params, device, lib=None):
-        """lib: object with the four sis3d_enet_* entry points (default: libsis3d_enet.so).  tests/test_enet_executor.py
-        passes a numpy model of the C contract (sis3d_enet.h) with device='cpu' to check this executor's wiring without a GPU."""
+        """lib: object with the four sis3d_enet_* entry points (default: libsis3d.so).  tests/test_enet_executor.py passes a
+        numpy model of the C contract (include/sis3d_enet.h) with device='cpu' to check this executor's wiring without a GPU."""
         self.dev = torch.device(device)
+        self._S = None
         if lib is None:
             if self.dev.type != "cuda":
-                raise RuntimeError("libsis3d_enet.so operates on CUDA memory (no CPU fallback)")
-            if not os.path.exists(_LIB):
-                raise ImportError(f"{_LIB} not found: build it with `make -C 3d-sis_b200/csrc/enet2d`")
-            lib = C.CDLL(_LIB)
+                raise RuntimeError("libsis3d.so operates on CUDA memory (no CPU fallback)")
+            from lib import _sis3d as S  # raises loudly when the library is missing
+            lib, self._S = S.lib, S
         self.lib = lib
         self.ops = []
         stream = self._stream()
@@ -64,12 +62,14 @@ class EnetEncoder:
             torch.cuda.current_stream().synchronize()
 
     def _stream(self):
+        if self._S is not None:
+            return self._S.stream()  # honours the stream slot pinned by the scene loop
         return C.c_void_p(torch.cuda.current_stream().cuda_stream) if self.dev.type == "cuda" else None
 
     @staticmethod
     def _check(rc):
         if rc != 0:
-            raise RuntimeError(f"libsis3d_enet call failed (code {rc})")
+            raise RuntimeError(f"libsis3d ENet call failed (code {rc})")
 
     def _conv(self, op, x, strides, n, h, w, out, out_ld, out_coff, res=None, res_c=0, res_ld=0, res_pool=0, slope=None):
         a = _Conv()

@@ -55,6 +55,20 @@ def _declare(root, dotted, shape, fan_in):
     mod.register_parameter(parts[-1], nn.Parameter(torch.empty(shape).uniform_(-bound, bound), requires_grad=False))
 
 
+def _declare_tensor(root, dotted, tensor, kind):
+    """Register `tensor` as parameter / buffer `dotted` on nested container modules (state_dict key == dotted)."""
+    parts = dotted.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if p not in mod._modules:
+            mod.add_module(p, nn.Module())
+        mod = mod._modules[p]
+    if kind == "param":
+        mod.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
+    else:
+        mod.register_buffer(parts[-1], tensor)
+
+
 class _MaskList:
     """Sequence of per-RoI mask tensors [1, num_classes, w, h, l] (the reference's `mask_pred[i]` list,
     lib/nets/network.py:303-317) as lazily created views of the packed [total_voxels, num_classes] output."""
@@ -182,9 +196,45 @@ class Network(nn.Module):
             # reference counting right away instead of by a later cyclic GC pass in the middle of someone else's capture
             self.mask_backbone._owner = weakref.ref(self)
         if cfg.USE_IMAGES and not cfg.USE_IMAGES_GT:
-            # the 2D ENet encoder is upstream of the hot path; callers feed ENet-shaped
-            # features (USE_IMAGES_GT semantics) or attach their own torch modules here.
-            self.image_enet_fixed = self.image_enet_trainable = None
+            self._declare_enet()
+
+    def _declare_enet(self):
+        """2-D ENet encoder (reference: network.py:62-63 -> enet.create_enet_for_3d, enet.py:697-715): parameters and
+        BatchNorm buffers under the reference's state_dict names (lib/nets/enet_keys.py), default-initialised, then overwritten
+        by cfg.PRETRAINED_ENET_PATH when that file exists (the reference loads it at this point too).  The forward runs on the
+        sis3d_enet_* kernels (lib/nets/enet.py); image_enet_classification is kept only for the checkpoint contract."""
+        from lib.nets.enet_keys import ENET_KEYS
+        n2d = int(cfg.NUM_2D_CLASSES)
+        names = {k[0] for k in ENET_KEYS}
+        enc = []
+        for name, shape, kind, dt in ENET_KEYS:
+            if name.startswith("image_enet_classification"):
+                shape = (n2d,) + tuple(shape[1:])
+            if dt == "int64":
+                t = torch.zeros(shape, dtype=torch.int64)
+            elif name.endswith("running_var"):
+                t = torch.ones(shape)
+            elif name.endswith(("running_mean", ".bias")):
+                t = torch.zeros(shape)
+            elif len(shape) == 4:
+                bound = 1.0 / math.sqrt(shape[1] * shape[2] * shape[3])
+                t = torch.empty(shape).uniform_(-bound, bound)
+            else:  # 1-D weight: BatchNorm scale (has running statistics beside it) or PReLU slope
+                t = torch.ones(shape) if name[:-len("weight")] + "running_mean" in names else torch.full(shape, 0.25)
+            _declare_tensor(self, name, t, kind)
+            if not name.startswith("image_enet_classification") and not name.endswith("num_batches_tracked"):
+                enc.append(name)
+        self.__dict__["_enet_names"] = enc
+        path = str(cfg.get("PRETRAINED_ENET_PATH", "") or "")
+        if path and os.path.exists(path):
+            src = torch.load(path, map_location="cpu")  # plain create_enet keys ('0.0.weight', ...), same order as ENET_KEYS
+            own = dict(self.named_parameters())
+            own.update(dict(self.named_buffers()))
+            if len(src) != len(ENET_KEYS):
+                raise S.Sis3dError(f"{path}: {len(src)} tensors, the ENet of lib/nets/enet.py has {len(ENET_KEYS)}")
+            with torch.no_grad():
+                for (name, _, _, _), v in zip(ENET_KEYS, src.values()):
+                    own[name].copy_(v)
 
     # ------------------------------------------------------------------ packed weights
     def load_state_dict(self, *a, **k):
@@ -205,7 +255,10 @@ class Network(nn.Module):
         return t[:numel]
 
     def _version(self):
-        return tuple((n, p._version, p.data_ptr()) for n, p in self.named_parameters())
+        v = tuple((n, p._version, p.data_ptr()) for n, p in self.named_parameters())
+        if self.__dict__.get("_enet_names"):  # BatchNorm statistics of the 2-D encoder are buffers
+            v += tuple((n, b._version, b.data_ptr()) for n, b in self.named_buffers())
+        return v
 
     MATH_MODES = {  # mode -> (static-stage conv math, mask-stage conv math)
         "exact": ("tf32x3", "fp16"),   # default: integer outputs equal the fp32 path, masks within 1e-3
@@ -239,8 +292,14 @@ class Network(nn.Module):
             return
         self._packed, self._packed_tc, self._packed_h, self._packed_x3 = {}, {}, {}, {}
         params = dict(self.named_parameters())
+        self.__dict__["_enet"] = None
+        if self.__dict__.get("_enet_names"):
+            from lib.nets.enet import EnetEncoder
+            sd = dict(params)
+            sd.update(dict(self.named_buffers()))
+            self.__dict__["_enet"] = EnetEncoder([sd[n].detach() for n in self._enet_names], d["_dev"])
         for name, p in params.items():
-            if not name.endswith(".weight"):
+            if not name.endswith(".weight") or name.startswith("image_enet_"):
                 continue
             base = name[:-7]
             w = p.detach().float().contiguous()
@@ -499,14 +558,14 @@ class Network(nn.Module):
             feats = fused["feats"]
         else:
             feats = blobs["nearest_images"]["images"][0]
-            if not cfg.USE_IMAGES_GT:
-                if getattr(self, "image_enet_fixed", None) is None:
-                    raise S.Sis3dError("USE_IMAGES_GT=False needs the 2D ENet encoder (upstream of the hot path, "
-                                       "SURVEY 8f2): attach torch modules as net.image_enet_fixed/_trainable or feed "
-                                       "ENet-shaped features with USE_IMAGES_GT=True")
-                with torch.no_grad():
-                    feats = self.image_enet_trainable(self.image_enet_fixed(feats.to(dev)))
             feats = feats.to(dev, torch.float32, non_blocking=True)
+        if not cfg.USE_IMAGES_GT:
+            # raw images [n,3,H,W] -> ENet features [n,128,H/8,W/8] on the sis3d_enet_* kernels (reference: network.py:204-205)
+            if self.__dict__.get("_enet") is None:
+                raise S.Sis3dError("USE_IMAGES_GT=False but the 2-D ENet encoder was not declared (init_modules with this cfg)")
+            tok = self._rec("enet_encoder")
+            feats = self._enet(feats)
+            self._rec_end(tok)
         n = feats.shape[0]
         if fused is None:
             # reference calling convention: precomputed, stacked index lists + killing_inds
@@ -789,8 +848,9 @@ class Network(nn.Module):
             self._rec_end(tok)
         return out
 
-    def _graph_state(self, key, dims, n_views, feat_c, dev):
-        """Static input buffers + captured graph of `_static_stage` for one input shape."""
+    def _graph_state(self, key, dims, n_views, feat_shape, dev):
+        """Static input buffers + captured graph of `_static_stage` for one input shape (feat_shape = shape of one view's
+        2-D input: [128,32,41] ENet features, or [3,256,328] images when the encoder is part of the graph)."""
         st = self._graphs.get(key)
         if st is not None:
             if next(reversed(self._graphs)) != key:
@@ -801,7 +861,7 @@ class Network(nn.Module):
         w, h = int(cfg.DEPTH_SHAPE[0]), int(cfg.DEPTH_SHAPE[1])
         st = dict(scene=torch.zeros(1, 2, *dims, dtype=torch.float32, device=dev))
         if cfg.USE_IMAGES:
-            st.update(feats=torch.zeros(n_views, feat_c, h, w, dtype=torch.float32, device=dev),
+            st.update(feats=torch.zeros(n_views, *feat_shape, dtype=torch.float32, device=dev),
                       depths=torch.zeros(n_views, h, w, dtype=torch.float32, device=dev),
                       vp=torch.zeros(n_views, 40, dtype=torch.float32, device=dev))
         st["graph"] = None
@@ -868,8 +928,6 @@ class Network(nn.Module):
         with torch.no_grad(), Network._UseSlot(self, slot):
             lists = cfg.USE_IMAGES and "proj_ind_3d" in blobs
             use_graph = self._use_graph and not (self._keep_debug or self._prof is not None or lists)
-            if cfg.USE_IMAGES and not cfg.USE_IMAGES_GT:
-                use_graph = False
             fused = None
             if cfg.USE_IMAGES and not lists:
                 imgs = blobs["nearest_images"]
@@ -880,7 +938,7 @@ class Network(nn.Module):
             h.update(use_graph=use_graph, fused=fused)
             if use_graph:
                 nv = fused["feats"].shape[0] if fused else 0
-                fc = fused["feats"].shape[1] if fused else 0
+                fc = tuple(fused["feats"].shape[1:]) if fused else ()
                 key = (dims, nv, fc, self._math)
                 seen = self._shape_seen[key] = self._shape_seen.get(key, 0) + 1
                 if seen < self._graph_after and key not in self._graphs:

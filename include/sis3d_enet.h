@@ -1,12 +1,10 @@
-/* sis3d_enet.h -- WORK IN PROGRESS for SURVEY row f2 (2-D ENet encoder, lib/nets/enet.py:130-590).
- *
- * NOT part of the round-1 product path: nothing in lib/ loads libsis3d_enet.so, no parity claim is made for it, and it has
- * not run on a GPU yet (the round's GPU budget was spent on the 3-D path).  It is compiled by build() so that it stays
- * buildable; tools/enet_check.py is the first thing to run on a B200 in round 2.
+/* sis3d_enet.h -- C ABI of the 2-D ENet encoder kernels of libsis3d.so (replaces the cuDNN nn.Sequential of
+ * lib/nets/enet.py:130-590 that lib/nets/network.py:204-205 runs in front of the back-projection when USE_IMAGES_GT=False).
  *
  * Layout: NHWC fp32 activations (channel stride 1, row stride `ld` >= C so that producers can write channel slices of a wider
  * tensor); the very first layer reads the NCHW image through explicit element strides.  BatchNorm is folded on the host
- * (lib/nets/enet_program.py), so every layer is conv + bias (+ residual) + PReLU. */
+ * (lib/nets/enet_program.py), so every layer is conv + bias (+ residual) + PReLU.  fp32 CUDA-core math (exact parity path).
+ * Return codes: 0 ok, -1 invalid argument, -2 CUDA launch error.  Nothing is allocated; re-entrant per stream. */
 #ifndef SIS3D_ENET_H
 #define SIS3D_ENET_H
 #include <stddef.h>

@@ -62,10 +62,52 @@ def _th(t):
 
 
 _installed = False
+EXT_CALLS = {"gpu_nms": 0, "roi_pooling_forward_cuda": 0}  # how often the rebound native entry points were used (gpu mode)
 
 
-def install():
-    """Install all shims and put the reference root on sys.path.  Idempotent."""
+def _libsis3d_ext_stubs():
+    """INTEGRATION.md section 2, executed: ctypes stubs with the signatures of the reference's two cffi extension modules
+    (`gpu_nms`: lib/layer_utils/nms/src/nms_cuda.h:1; `roi_pooling_forward_cuda`: lib/layer_utils/roi_pooling/src/
+    roi_pooling_cuda.h:1-2) over the C ABI of libsis3d.so."""
+    lib = ctypes.CDLL(os.path.join(os.path.dirname(_HERE), "3d-sis_b200", "lib", "libsis3d.so"))
+    lib.sis3d_nms_workspace_bytes.restype = ctypes.c_size_t
+    lib.sis3d_strerror.restype = ctypes.c_char_p
+
+    def gpu_nms(keep, num_out, boxes, thresh):  # keep / num_out: CPU LongTensors, boxes: CUDA [N,6] sorted by score
+        EXT_CALLS["gpu_nms"] += 1
+        n = boxes.size(0)
+        boxes = boxes.contiguous().float()
+        ws = torch.empty(max(int(lib.sis3d_nms_workspace_bytes(n)), 8), dtype=torch.uint8, device=boxes.device)
+        keep_d = torch.empty(max(n, 1), dtype=torch.int64, device=boxes.device)
+        num_d = torch.zeros(1, dtype=torch.int32, device=boxes.device)
+        rc = lib.sis3d_nms(ctypes.c_void_p(boxes.data_ptr()), n, ctypes.c_float(thresh), ctypes.c_void_p(keep_d.data_ptr()),
+                           ctypes.c_void_p(num_d.data_ptr()), ctypes.c_void_p(ws.data_ptr()),
+                           ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc:
+            raise RuntimeError(lib.sis3d_strerror(rc).decode())
+        k = int(num_d.item())
+        num_out[0] = k
+        keep[:k] = keep_d[:k].cpu()
+        return 1
+
+    def roi_pooling_forward_cuda(pw, ph, pl, scale, features, rois, output, argmax):
+        EXT_CALLS["roi_pooling_forward_cuda"] += 1
+        _, C, W, H, L = features.size()
+        features, rois = features.contiguous(), rois.contiguous().float()
+        rc = lib.sis3d_roi_pool_fwd(ctypes.c_void_p(features.data_ptr()), 0, ctypes.c_float(scale), rois.size(0), W, H, L, C,
+                                    int(pw), int(ph), int(pl), ctypes.c_void_p(rois.data_ptr()),
+                                    ctypes.c_void_p(output.data_ptr()), ctypes.c_void_p(argmax.data_ptr()),
+                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        return 1 if rc == 0 else 0
+
+    return gpu_nms, roi_pooling_forward_cuda
+
+
+def install(gpu=False):
+    """Install all shims and put the reference root on sys.path.  Idempotent.
+    gpu=False: everything on the CPU (`.cuda()` no-ops; numpy NMS, the reference's CPU RoI-pooling C kernel).
+    gpu=True : the reference's Python runs on the GPU as written (cuDNN convs in fp32) and its two native extensions are the
+               ctypes stubs of INTEGRATION.md section 2 bound to libsis3d.so -- the drop-in test of the operator boundary."""
     global _installed
     if _installed:
         return
@@ -100,16 +142,27 @@ def install():
                                            ctypes.byref(_th(f)), ctypes.byref(_th(r)), ctypes.byref(_th(o)))
 
     ext_roi = stub("lib.layer_utils.roi_pooling._ext")
-    ext_roi.roi_pooling = stub("lib.layer_utils.roi_pooling._ext.roi_pooling",
-                               roi_pooling_forward=roi_pooling_forward)
     ext_nms = stub("lib.layer_utils.nms._ext")
-    ext_nms.nms = stub("lib.layer_utils.nms._ext.nms")
+    if gpu:
+        gpu_nms, roi_fwd_cuda = _libsis3d_ext_stubs()
+        ext_roi.roi_pooling = stub("lib.layer_utils.roi_pooling._ext.roi_pooling", roi_pooling_forward=roi_pooling_forward,
+                                   roi_pooling_forward_cuda=roi_fwd_cuda)
+        ext_nms.nms = stub("lib.layer_utils.nms._ext.nms", gpu_nms=gpu_nms)
+        # torch-0.4 semantics the reference relies on: np.where(<cuda tensor>) copies to the host implicitly
+        # (proposal_layer.py:36-43); fp32 convolutions (no TF32 inside cuDNN / cuBLAS)
+        _arr = torch.Tensor.__array__
+        torch.Tensor.__array__ = lambda self, *a, **k: _arr(self.detach().cpu() if self.is_cuda else self, *a, **k)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    else:
+        ext_roi.roi_pooling = stub("lib.layer_utils.roi_pooling._ext.roi_pooling", roi_pooling_forward=roi_pooling_forward)
+        ext_nms.nms = stub("lib.layer_utils.nms._ext.nms")
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.nn.Module.cuda = lambda self, *a, **k: self
+        torch.cuda.synchronize = lambda *a, **k: None
+        torch.cuda.empty_cache = lambda *a, **k: None
 
     # runtime patches ----------------------------------------------------------------------------
-    torch.Tensor.cuda = lambda self, *a, **k: self
-    torch.nn.Module.cuda = lambda self, *a, **k: self
-    torch.cuda.synchronize = lambda *a, **k: None
-    torch.cuda.empty_cache = lambda *a, **k: None
     _truediv = torch.Tensor.__truediv__
 
     def _div(self, other):
@@ -148,9 +201,9 @@ def install():
     _installed = True
 
 
-def load_cfg(yml_rel, **over):
+def load_cfg(yml_rel, gpu=False, **over):
     """cfg_from_file + NUM_CLASSES as derived by main.py:44-50."""
-    install()
+    install(gpu)
     from lib.utils.config import cfg, cfg_from_file
     cfg_from_file(os.path.join(REF, "experiments", "cfgs", yml_rel))
     cfg.NUM_CLASSES = 26 if 'SUNCG' in yml_rel else 19  # = #labels with weight>0 in cfg.LABEL_MAP (main.py:44-50)

@@ -17,6 +17,35 @@ def test_header_symbols_exported():
     assert S.lib.sis3d_strerror(-3).decode() == "workspace too small"
 
 
+def test_enet_header_symbols_exported():
+    from lib import _sis3d as S
+    hdr = open(os.path.join(ROOT, "include", "sis3d_enet.h")).read()
+    declared = set(re.findall(r"\b(sis3d_enet_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(S.SYMBOLS_ENET)
+    assert not [s for s in sorted(declared) if not hasattr(S.lib, s)]
+
+
+def test_enet_state_dict_contract():
+    """USE_IMAGES_GT=False: the 2-D encoder's parameters and BatchNorm buffers appear under the reference's state_dict names
+    (lib/nets/enet_keys.py, generated from the unmodified reference) with the reference's shapes, in its order."""
+    from lib.nets.enet_keys import ENET_KEYS
+    from lib.utils.config import cfg, cfg_from_file, cfg_reset
+    cfg_reset()
+    cfg_from_file(os.path.join(ROOT, "3d-sis_b200", "experiments", "cfgs", "ScanNet", "rpn_class_mask_5.yml"))
+    cfg.NUM_CLASSES, cfg.USE_IMAGES, cfg.USE_IMAGES_GT = 19, True, False
+    from lib.nets import backbones
+    net = getattr(backbones, cfg.NET)()
+    net.init_modules()
+    sd = net.state_dict()
+    enet_keys = [k for k in sd if k.startswith("image_enet_")]
+    assert enet_keys == [k[0] for k in ENET_KEYS]
+    for name, shape, kind, dt in ENET_KEYS:
+        want = (int(cfg.NUM_2D_CLASSES),) + tuple(shape[1:]) if name.startswith("image_enet_classification") else tuple(shape)
+        assert tuple(sd[name].shape) == want, name
+    assert len(net._enet_names) == 429  # encoder tensors the kernels consume (no num_batches_tracked, no classifier)
+    cfg_reset()
+
+
 def test_region_struct_layout():
     from lib import _sis3d as S
     assert S.REGION_BYTES == 104  # 3*8 + 3*4 + 3*4 + 3*8 + 3*8 + 4 + 4
