@@ -129,10 +129,17 @@ __device__ __forceinline__ void tmem_ld32_add(uint32_t taddr, float *v) {  // v 
 template <int X3>
 __device__ __forceinline__ void acc_ld32(uint32_t taddr, int n_main, uint32_t stride, uint32_t lo_off, float *v) {
     tmem_ld32(taddr, v);
-    if constexpr (X3) {
+    if constexpr (X3 != 0) {
         if (n_main > 1) tmem_ld32_add(taddr + stride, v);
         if (n_main > 2) tmem_ld32_add(taddr + 2 * stride, v);
-        tmem_ld32_add(taddr + lo_off, v);
+        if constexpr (X3 == 2) {  // fp16 split: the low parts were stored scaled by 2^11, so are the cross terms
+            float t[32];
+            tmem_ld32(taddr + lo_off, t);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaf(t[i], 1.0f / 2048.0f, v[i]);
+        } else {
+            tmem_ld32_add(taddr + lo_off, v);
+        }
     }
 }
 
@@ -147,6 +154,30 @@ __device__ __forceinline__ void split_tf32(float v, float &hi, float &lo) {
     lo = tf32_rna_bits(v - hi);
 }
 
+// fp16 split (X3 = 2): v = hi + lo / 2048 with hi = fp16(v) (round to nearest) and lo = fp16((v - hi) * 2048): the same
+// 11 + 11 significand bits as the TF32 split, but the MMAs run at the fp16 rate (2.5x the measured TF32 rate on B200).
+// Scaling the low part keeps it out of fp16's subnormal range; |v| is clamped to the fp16 range first.
+__device__ __forceinline__ void split_f16(float v, __half &hi, __half &lo) {
+    v = fminf(fmaxf(v, -65504.f), 65504.f);
+    hi = __float2half_rn(v);
+    lo = __float2half_rn((v - __half2float(hi)) * 2048.0f);
+}
+// activations, two at a time with packed conversions (4 ALU ops per element); precondition |v| < 65504 (not clamped here: the
+// fp16-operand mask stage of the default math mode has the same range requirement)
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn((a - hf.x) * 2048.0f, (b - hf.y) * 2048.0f);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+__device__ __forceinline__ void split_f16x8(const float4 a, const float4 b, uint4 &hi, uint4 &lo) {
+    split_f16x2(a.x, a.y, hi.x, lo.x);
+    split_f16x2(a.z, a.w, hi.y, lo.y);
+    split_f16x2(b.x, b.y, hi.z, lo.z);
+    split_f16x2(b.z, b.w, hi.w, lo.w);
+}
+
 // stages: 4 for BN = 128 (128 KB), 3 for BN <= 64 so that three CTAs fit one SM (the grids of the narrow layers are
 // ~1.3-1.5 waves at two CTAs/SM)
 template <int BN>
@@ -154,15 +185,21 @@ struct TcStages { static constexpr int value = BN >= 128 ? 4 : 3; };
 // stage count per kernel flavour: the 3x3x3 stages are 3x bigger (slab + three weight tiles)
 // X3 (error-compensated 3xTF32, 64-byte K rows): every stage also holds the low parts of A and B; BN = 32 keeps three
 // stages (96 KB, two CTAs per SM), BN = 64 two (88 KB, two CTAs per SM), BN = 128 three (204 KB)
-template <int BN, int KS, int ROWB, int X3 = 0>
+// X3 = 2 (fp16 split, 128-byte fp32 source rows): a stage = fp32 landing slab + fp16 hi/lo slabs + fp16 hi/lo weight tiles;
+// BN = 32: two stages (104 KB: two CTAs share an SM, one's prologue/epilogue under the other's main loop; the 64-wide fused tail's
+// W3 tiles push that 1.5 KB over the limit, so it runs one CTA with four stages), BN = 64: three, BN = 128: two (176 KB)
+template <int BN, int KS, int ROWB, int X3 = 0, int N2 = 0>
 struct TcStagesOf {
-    static constexpr int value = KS == 3 ? (X3 ? (BN == 64 ? 2 : 3) : (BN >= 128 ? 3 : 2)) : TcStages<BN>::value;
+    static constexpr int value =
+        X3 == 2 ? (KS == 3 ? (BN == 32 ? (N2 == 64 ? 4 : 2) : BN == 64 ? 3 : 2) : (BN >= 128 ? 4 : 3))
+                : (KS == 3 ? (X3 ? (BN == 64 ? 2 : 3) : (BN >= 128 ? 3 : 2)) : TcStages<BN>::value);
 };  // narrow 3x3x3 layers: 2 stages so 2-3 CTAs share an SM
 template <int BN, int KS, int ROWB, int BY, int N2 = 0, int X3 = 0>
 constexpr size_t tc_smem_bytes() {
-    return (size_t)TcStagesOf<BN, KS, ROWB, X3>::value * (1 + X3) *
-               ((KS == 3 ? (16 / BY + 2) * BY * TC_BZ : TC_BM) * ROWB + (KS == 3 ? 3 : 1) * BN * ROWB) +
-           (size_t)(1 + X3) * N2 * 128 * (BN / 32) + 1024 + 256;
+    // bytes of one weight row in shared memory: ROWB, or 64 (32 fp16 channels) in the fp16-split mode
+    return (size_t)TcStagesOf<BN, KS, ROWB, X3, N2>::value * (X3 ? 2 : 1) *
+               ((KS == 3 ? (16 / BY + 2) * BY * TC_BZ : TC_BM) * ROWB + (KS == 3 ? 3 : 1) * BN * (X3 == 2 ? 64 : ROWB)) +
+           (size_t)(X3 == 1 ? 2 : 1) * N2 * 128 * (BN / 32) + 1024 + 256;
 }
 constexpr int tc_tmem_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
 
@@ -183,12 +220,25 @@ constexpr int tc_tmem_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 12
 // to the MMA's async proxy with fence.proxy.async + the conv_done mbarrier.  No extra L2->SM traffic for activations; the
 // tensor pipe, which the narrow layers leave mostly idle, does 3x the MMAs.  Result: fp32-class accuracy (the integer
 // outputs of the detector -- top-N order, NMS keep lists, class argmax, crop bounds -- match the fp32 path) on tcgen05.
+//
+// X3 = 2 (EB = 4, ROWB = 128): the same compensation with an fp16 split (split_f16 above): the fp32 slab lands in a staging
+// buffer, warps 2-3 write its hi and (scaled) lo parts as two fp16 K-major SWIZZLE_64B tiles, the weights are pre-split fp16
+// tiles, and the three products are kind::f16 MMAs -- same 22 significand bits, 2.5x the MMA rate, half as many stages.
 template <int BN, int KS, int EB = 4, int ROWB = 128, int BY = 2, int N2 = 0, int X3 = 0>
-__global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(X3 == 2 ? 256 : 128, (X3 == 2 && BN == 32) ? 2 : 1) conv3d_k3_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
                                                               const __grid_constant__ CUtensorMap tmB2, const TcArgs a) {
     static_assert(N2 == 0 || (KS == 3 && EB == 4), "conv3 fusion: TF32 3x3x3 kernels only");
     static_assert(X3 == 0 || EB == 4, "3xTF32 splits fp32-stored operands");
+    static_assert(X3 != 2 || ROWB == 128, "the fp16 split reads 128-byte fp32 rows and writes 64-byte fp16 rows");
+    constexpr bool XH = X3 == 2;             // fp16 split
+    // threads: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2.. = operand splitters (X3), every warp = epilogue.  The fp16
+    // split re-lays the slab out (fp32 128-byte rows -> two fp16 64-byte-row tiles), ~4 ALU ops per element: six splitter warps
+    // keep it below the MMA time of a stage (two were 2x slower than the tensor pipe)
+    constexpr int NT = XH ? 256 : 128;
+    constexpr int NSPLIT = NT - 64;          // splitter threads
+    constexpr int NHALF = NT / 128;          // epilogue: warps w and w + 4 share TMEM lane quarter w % 4 and alternate column chunks
+    constexpr int OPB = XH ? 64 : ROWB;      // bytes of one K-slice row of the MMA operands in shared memory
     constexpr int KC = ROWB / EB;            // channels per pipeline stage
     constexpr int TC_BY = BY, TC_BX = 16 / BY;  // brick: BY = 2 -> 8x2x8 (whole volumes), BY = 4 -> 4x4x8 (small RoI crops)
     // 3x3x3: one stage = one (dy, dz) pair: an x-halo slab of (8+2) x-planes (160 rows) serves the three x-taps --
@@ -196,14 +246,17 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
     constexpr int XT = KS == 3 ? 3 : 1;      // x-taps per stage
     constexpr int A_ROWS = KS == 3 ? (TC_BX + 2) * TC_BY * TC_BZ : TC_BM;
     constexpr int A_BYTES = A_ROWS * ROWB;
-    constexpr int B_BYTES = BN * ROWB;
-    // stage layout: [A | A_lo (X3) | B x XT | B_lo x XT (X3)]
-    constexpr int B_OFF = (1 + X3) * A_BYTES;
-    constexpr int STAGE_BYTES = (1 + X3) * (A_BYTES + XT * B_BYTES);
-    constexpr int TC_STAGES = TcStagesOf<BN, KS, ROWB, X3>::value;
+    constexpr int B_BYTES = BN * OPB;
+    // stage layout: X3 = 0: [A | B x XT];  X3 = 1: [A_hi (in place) | A_lo | B_hi x XT | B_lo x XT];
+    //               X3 = 2: [A fp32 (staging) | A_hi fp16 | A_lo fp16 | B_hi x XT | B_lo x XT]  (fp16 tiles: half of A_BYTES each)
+    constexpr int B_OFF = (X3 ? 2 : 1) * A_BYTES;
+    constexpr int STAGE_BYTES = (X3 ? 2 : 1) * (A_BYTES + XT * B_BYTES);
+    constexpr int TC_STAGES = TcStagesOf<BN, KS, ROWB, X3, N2>::value;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B needs 1024 B alignment
-    constexpr int B2_BYTES = (1 + X3) * N2 * 128 * (BN / 32);  // W3 as BN/32 K slices of [N2 rows][32 ch] (X3: hi slices, then lo)
+    // W3 as BN/32 K slices of [N2 rows][32 ch] (X3: hi slices, then lo slices; fp16 split: 64-byte rows)
+    constexpr int B2_SLICE = N2 * (XH ? 64 : 128);
+    constexpr int B2_BYTES = (X3 ? 2 : 1) * B2_SLICE * (BN / 32);
     // X3 accumulators: the tensor core adds into its fp32 accumulator with truncation, a bias that grows with the length of the
     // accumulation chain -- invisible next to TF32 operand rounding, but the dominant error of the compensated product.  So the
     // hi.hi terms rotate over THREE accumulators (stage it -> it % 3: chains a third as long, summed with round-to-nearest adds in
@@ -220,7 +273,7 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
 
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); mbar_init(conv_done + i, 64); }
+        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); mbar_init(conv_done + i, NSPLIT); }
         mbar_init(acc_ready, 1);
         mbar_init(b2_full, 1);
         mbar_init(acc2_ready, 1);
@@ -263,16 +316,16 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
         if constexpr (N2 > 0) {
             mbar_expect_tx(b2_full, B2_BYTES);
 #pragma unroll
-            for (int h = 0; h <= X3; ++h)  // X3: rows [N2, 2 N2) of the split W3 are the low parts
+            for (int h = 0; h < (X3 ? 2 : 1); ++h)  // X3: rows [N2, 2 N2) of the split W3 are the low parts
 #pragma unroll
                 for (int kc = 0; kc < BN / 32; ++kc)
-                    tma_load_2d(smem_b2 + (h * (BN / 32) + kc) * N2 * 128, &tmB2, b2_full, kc * 32, h * N2);
+                    tma_load_2d(smem_b2 + (h * (BN / 32) + kc) * B2_SLICE, &tmB2, b2_full, kc * 32, h * N2);
         }
         for (int it = 0; it < total; ++it) {
             const int s = it % TC_STAGES;
             const uint32_t ph = (it / TC_STAGES) & 1;
             mbar_wait(empty + s, ph ^ 1);
-            mbar_expect_tx(full + s, STAGE_BYTES - X3 * A_BYTES);  // X3: A_lo is written by the converter warps, not by TMA
+            mbar_expect_tx(full + s, STAGE_BYTES - (X3 ? A_BYTES : 0));  // X3: the split tiles are written by warps 2-3, not by TMA
             const int tap = it / kchunks, kc = it - tap * kchunks;
             uint8_t *sa = smem + s * STAGE_BYTES;
             if constexpr (KS == 0) {
@@ -305,7 +358,7 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
         // ===== MMA issuer =====
         // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
         // A,B K-major, N>>3 at [17,23), M>>4 at [24,29)
-        constexpr uint32_t fmt = EB == 4 ? 2u : 0u;  // F16F32Format: 2 = TF32, 0 = F16
+        constexpr uint32_t fmt = (EB == 4 && !XH) ? 2u : 0u;  // F16F32Format: 2 = TF32, 0 = F16
         const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
         for (int it = 0; it < total; ++it) {
             const int s = it % TC_STAGES;
@@ -313,19 +366,28 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
             mbar_wait(X3 ? conv_done + s : full + s, ph);  // X3: the split (which itself waited for the TMA) is done
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + B_OFF;
+            // operand tiles: X3 = 1: hi at sa (in place), lo at sa + A_BYTES; X3 = 2: fp16 hi at sa + A_BYTES, lo half an A_BYTES on
+            const uint32_t a_hi = sa + (XH ? A_BYTES : 0), a_lo = sa + A_BYTES + (XH ? A_BYTES / 2 : 0);
 #pragma unroll
             for (int dx = 0; dx < XT; ++dx) {
                 // x-tap dx: A rows start 16 rows (= two 8-row swizzle atoms) further into the slab
-                const uint32_t ax = sa + dx * (TC_BY * TC_BZ) * ROWB, bx = sb + dx * B_BYTES;
+                const uint32_t ax = a_hi + dx * (TC_BY * TC_BZ) * OPB, al_x = a_lo + dx * (TC_BY * TC_BZ) * OPB, bx = sb + dx * B_BYTES;
 #pragma unroll
-                for (int k = 0; k < ROWB / 32; ++k) {  // one MMA consumes 32 B of K (8 tf32 / 16 f16): advance inside the swizzle atom
+                for (int k = 0; k < OPB / 32; ++k) {  // one MMA consumes 32 B of K (8 tf32 / 16 f16): advance inside the swizzle atom
                     const uint32_t acc = (it | dx | k) ? 1u : 0u;
                     if constexpr (X3) {  // cross terms A_lo.B_hi + A_hi.B_lo -> accumulator 3; A_hi.B_hi -> accumulator it % 3
-                        const uint64_t ah = umma_desc<ROWB>(ax + k * 32), al = umma_desc<ROWB>(ax + A_BYTES + k * 32);
-                        const uint64_t bh = umma_desc<ROWB>(bx + k * 32), bl = umma_desc<ROWB>(bx + XT * B_BYTES + k * 32);
-                        umma_tf32(tmem_base + 3 * BN, al, bh, idesc, acc);
-                        umma_tf32(tmem_base + 3 * BN, ah, bl, idesc, 1u);
-                        umma_tf32(tmem_base + (uint32_t)((it % 3) * BN), ah, bh, idesc, ((it >= 3) | dx | k) ? 1u : 0u);
+                        const uint64_t ah = umma_desc<OPB>(ax + k * 32), al = umma_desc<OPB>(al_x + k * 32);
+                        const uint64_t bh = umma_desc<OPB>(bx + k * 32), bl = umma_desc<OPB>(bx + XT * B_BYTES + k * 32);
+                        const uint32_t dm = tmem_base + (uint32_t)((it % 3) * BN), acc_m = ((it >= 3) | dx | k) ? 1u : 0u;
+                        if constexpr (XH) {
+                            umma_f16(tmem_base + 3 * BN, al, bh, idesc, acc);
+                            umma_f16(tmem_base + 3 * BN, ah, bl, idesc, 1u);
+                            umma_f16(dm, ah, bh, idesc, acc_m);
+                        } else {
+                            umma_tf32(tmem_base + 3 * BN, al, bh, idesc, acc);
+                            umma_tf32(tmem_base + 3 * BN, ah, bl, idesc, 1u);
+                            umma_tf32(dm, ah, bh, idesc, acc_m);
+                        }
                     } else if constexpr (EB == 4) umma_tf32(tmem_base, umma_desc<ROWB>(ax + k * 32), umma_desc<ROWB>(bx + k * 32), idesc, acc);
                     else umma_f16(tmem_base, umma_desc<ROWB>(ax + k * 32), umma_desc<ROWB>(bx + k * 32), idesc, acc);
                 }
@@ -334,20 +396,40 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
         }
         umma_commit(acc_ready);
     } else if (X3 && warp >= 2) {
-        // ===== operand splitter (warps 2-3): slab -> hi (in place) + lo (second buffer), same swizzled layout =====
+        // ===== operand splitter (warps 2-3) =====
         const int t = threadIdx.x - 64;
         for (int it = 0; it < total; ++it) {
             const int s = it % TC_STAGES;
             mbar_wait(full + s, (it / TC_STAGES) & 1);
-            float4 *hi = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES);
-            float4 *lo = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES + A_BYTES);
+            uint8_t *st = smem + s * STAGE_BYTES;
+            if constexpr (XH) {
+                // fp32 slab (128-byte rows, SWIZZLE_128B: 16-byte chunk j of row r at r*128 + ((j ^ (r & 7)) << 4)) ->
+                // fp16 hi / lo tiles (64-byte rows, SWIZZLE_64B: chunk q of row r at r*64 + ((q ^ ((r >> 1) & 3)) << 4));
+                // one work item = 8 channels of one row = source chunks 2q, 2q+1 -> destination chunk q
+                uint8_t *hi = st + A_BYTES, *lo = st + A_BYTES + A_BYTES / 2;
 #pragma unroll 2
-            for (int i = t; i < A_BYTES / 16; i += 64) {
-                const float4 v = hi[i];
-                float4 h, l;
-                split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-                hi[i] = h;
-                lo[i] = l;
+                for (int i = t; i < A_ROWS * 4; i += NSPLIT) {
+                    const int r = i >> 2, q = i & 3;
+                    const float4 v0 = *reinterpret_cast<const float4 *>(st + r * 128 + (((2 * q) ^ (r & 7)) << 4));
+                    const float4 v1 = *reinterpret_cast<const float4 *>(st + r * 128 + (((2 * q + 1) ^ (r & 7)) << 4));
+                    uint4 h, l;
+                    split_f16x8(v0, v1, h, l);
+                    const int d = r * 64 + ((q ^ ((r >> 1) & 3)) << 4);
+                    *reinterpret_cast<uint4 *>(hi + d) = h;
+                    *reinterpret_cast<uint4 *>(lo + d) = l;
+                }
+            } else {
+                // slab -> hi (in place) + lo (second buffer): the split is elementwise, so the swizzled layout is untouched
+                float4 *hi = reinterpret_cast<float4 *>(st);
+                float4 *lo = reinterpret_cast<float4 *>(st + A_BYTES);
+#pragma unroll 2
+                for (int i = t; i < A_BYTES / 16; i += NSPLIT) {
+                    const float4 v = hi[i];
+                    float4 h, l;
+                    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+                    hi[i] = h;
+                    lo[i] = l;
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA's async proxy
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(conv_done + s)) : "memory");
@@ -358,12 +440,12 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
         // ===== GEMM epilogue: raw fp32 partial sums of this K split -> partial[z][m][n] (bias/ReLU in the reduce pass)
         if (total > 0) mbar_wait(acc_ready, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int m = x0 + (int)threadIdx.x;
+        const int m = x0 + (int)(threadIdx.x & 127);
         float *prow = a.out + ((int64_t)blockIdx.z * a.gemm_m + m) * a.out_ld + n0;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = (int)(threadIdx.x >> 7); c < BN / 32; c += NHALF) {
             float v[32];
-            acc_ld32<X3>(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), min(total, 3), BN, 3 * BN, v);
+            acc_ld32<X3>(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(c * 32), min(total, 3), BN, 3 * BN, v);
             if (m < a.gemm_m) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
@@ -380,18 +462,22 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
     // ===== epilogue: TMEM lane r == output row r of the brick =====
     mbar_wait(acc_ready, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int r = threadIdx.x;
+    const int r = threadIdx.x & 127, half = threadIdx.x >> 7;  // row of the brick / which half of the column chunks
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t acc_col = 0;  // first TMEM column of the accumulator the store loop reads
     if constexpr (N2 > 0) {
         // conv2's tile -> ReLU -> shared memory as the A operand of the 1x1 conv: row r, 16-byte chunk j of K slice kc at
         // kc*16 KB + r*128 + ((j ^ (r & 7)) << 4)  (the canonical SWIZZLE_128B K-major layout TMA would have produced)
         uint8_t *a2 = smem;  // aliases the pipeline stages: every TMA write landed and every MMA reading them retired
-        constexpr int A2_BYTES = (BN / 32) * (TC_BM * 128);  // X3: the low parts follow as a second tile of the same layout
+        // one K slice (32 channels) of the A operand of the 1x1 conv: 128 rows x 128 B (fp32 / TF32 split) or x 64 B (fp16 split);
+        // X3: the low parts follow as a second set of slices of the same layout
+        constexpr int A2_SLICE = TC_BM * (XH ? 64 : 128);
+        constexpr int A2_BYTES = (BN / 32) * A2_SLICE;
 #pragma unroll 1
-        for (int kc = 0; kc < BN / 32; ++kc) {
+        for (int kc = half; kc < BN / 32; kc += NHALF) {
             float v[32];
-            acc_ld32<X3>(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(kc * 32), min(total, 3), BN, 3 * BN, v);
-            uint8_t *row = a2 + kc * (TC_BM * 128) + r * 128;
+            acc_ld32<X3>(tmem_base + lane_base + (uint32_t)(kc * 32), min(total, 3), BN, 3 * BN, v);
+            uint8_t *row = a2 + kc * A2_SLICE + r * (XH ? 64 : 128);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -400,7 +486,9 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
                     o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                 }
                 o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
-                if constexpr (X3) {
+                if constexpr (XH) {
+                    v[4 * j] = o.x; v[4 * j + 1] = o.y; v[4 * j + 2] = o.z; v[4 * j + 3] = o.w;  // split below, 8 channels per chunk
+                } else if constexpr (X3 == 1) {
                     float4 h, l;
                     split_tf32(o.x, h.x, l.x); split_tf32(o.y, h.y, l.y); split_tf32(o.z, h.z, l.z); split_tf32(o.w, h.w, l.w);
                     *reinterpret_cast<float4 *>(row + ((j ^ (r & 7)) << 4)) = h;
@@ -409,27 +497,46 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
                     *reinterpret_cast<float4 *>(row + ((j ^ (r & 7)) << 4)) = o;
                 }
             }
+            if constexpr (XH) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {  // 16-byte chunk q = channels 8q..8q+7 of this slice, SWIZZLE_64B position
+                    uint4 h, l;
+                    split_f16x8(make_float4(v[8 * q], v[8 * q + 1], v[8 * q + 2], v[8 * q + 3]),
+                                make_float4(v[8 * q + 4], v[8 * q + 5], v[8 * q + 6], v[8 * q + 7]), h, l);
+                    const int d = (q ^ ((r >> 1) & 3)) << 4;
+                    *reinterpret_cast<uint4 *>(row + d) = h;
+                    *reinterpret_cast<uint4 *>(row + A2_BYTES + d) = l;
+                }
+            }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA's async proxy
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (threadIdx.x == 32) {
-            const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N2 >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            constexpr uint32_t fmt2 = XH ? 0u : 2u;
+            const uint32_t idesc2 = (1u << 4) | (fmt2 << 7) | (fmt2 << 10) | ((uint32_t)(N2 >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             mbar_wait(b2_full, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa2 = smem_u32(a2), sb2 = smem_u32(smem_b2);
+            constexpr int OP2 = XH ? 64 : 128;
 #pragma unroll
             for (int kc = 0; kc < BN / 32; ++kc)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint64_t ah = umma_desc<128>(sa2 + kc * (TC_BM * 128) + k * 32), bh = umma_desc<128>(sb2 + kc * (N2 * 128) + k * 32);
+                for (int k = 0; k < OP2 / 32; ++k) {
+                    const uint64_t ah = umma_desc<OP2>(sa2 + kc * A2_SLICE + k * 32), bh = umma_desc<OP2>(sb2 + kc * B2_SLICE + k * 32);
                     if constexpr (X3) {
-                        const uint64_t al = umma_desc<128>(sa2 + A2_BYTES + kc * (TC_BM * 128) + k * 32);
-                        const uint64_t bl = umma_desc<128>(sb2 + (BN / 32 + kc) * (N2 * 128) + k * 32);
-                        umma_tf32(tmem_base + 4 * BN + N2, al, bh, idesc2, (kc | k) ? 1u : 0u);
-                        umma_tf32(tmem_base + 4 * BN + N2, ah, bl, idesc2, 1u);
-                        umma_tf32(tmem_base + 4 * BN, ah, bh, idesc2, (kc | k) ? 1u : 0u);
+                        const uint64_t al = umma_desc<OP2>(sa2 + A2_BYTES + kc * A2_SLICE + k * 32);
+                        const uint64_t bl = umma_desc<OP2>(sb2 + (BN / 32 + kc) * B2_SLICE + k * 32);
+                        if constexpr (XH) {
+                            umma_f16(tmem_base + 4 * BN + N2, al, bh, idesc2, (kc | k) ? 1u : 0u);
+                            umma_f16(tmem_base + 4 * BN + N2, ah, bl, idesc2, 1u);
+                            umma_f16(tmem_base + 4 * BN, ah, bh, idesc2, (kc | k) ? 1u : 0u);
+                        } else {
+                            umma_tf32(tmem_base + 4 * BN + N2, al, bh, idesc2, (kc | k) ? 1u : 0u);
+                            umma_tf32(tmem_base + 4 * BN + N2, ah, bl, idesc2, 1u);
+                            umma_tf32(tmem_base + 4 * BN, ah, bh, idesc2, (kc | k) ? 1u : 0u);
+                        }
                     } else {
                         umma_tf32(tmem_base + BN, ah, bh, idesc2, (kc | k) ? 1u : 0u);
                     }
@@ -449,10 +556,10 @@ __global__ void __launch_bounds__(128, 1) conv3d_k3_tc_kernel(const __grid_const
     __half *hrow = a.out16 ? a.out16 + vox * a.out_ld + a.out_coff + n0 : nullptr;
     const float *rrow = a.res ? a.res + vox * a.res_ld + a.res_coff + n0 : nullptr;
 #pragma unroll 1
-    for (int c = 0; c < NOUT / 32; ++c) {
+    for (int c = half; c < NOUT / 32; c += NHALF) {
         float v[32];
-        if constexpr (N2 > 0) acc_ld32<X3>(tmem_base + ((uint32_t)(warp * 32) << 16) + acc_col + (uint32_t)(c * 32), 1, 0, N2, v);
-        else acc_ld32<X3>(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), min(total, 3), BN, 3 * BN, v);
+        if constexpr (N2 > 0) acc_ld32<X3>(tmem_base + lane_base + acc_col + (uint32_t)(c * 32), 1, 0, N2, v);
+        else acc_ld32<X3>(tmem_base + lane_base + (uint32_t)(c * 32), min(total, 3), BN, 3 * BN, v);
         if (valid) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -518,6 +625,20 @@ __global__ void pack_conv_weight_tc_x3_kernel(const float *w, int cout, int cin,
     }
 }
 
+// fp16-split weights: rows [0, cout) = fp16(w), rows [cout, 2 cout) = fp16((w - fp16(w)) * 2048); same k order
+__global__ void pack_conv_weight_tc_h3_kernel(const float *w, int cout, int cin, int taps, __half *out) {
+    const int64_t total = (int64_t)cout * taps * cin;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cin);
+        const int tap = (int)((i / cin) % taps);
+        const int n = (int)(i / ((int64_t)cin * taps));
+        __half hi, lo;
+        split_f16(w[((int64_t)n * cin + c) * taps + tap], hi, lo);
+        out[i] = hi;
+        out[total + i] = lo;
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -543,7 +664,7 @@ static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcArg
         attr_done = true;
     }
     dim3 grid(n_tiles, N2 > 0 ? 1 : a.cout / BN, grid_z);
-    conv3d_k3_tc_kernel<BN, KS, EB, ROWB, BY, N2, X3><<<grid, 128, smem, s>>>(tmA, tmB, tmB2 ? *tmB2 : tmB, a);
+    conv3d_k3_tc_kernel<BN, KS, EB, ROWB, BY, N2, X3><<<grid, X3 == 2 ? 256 : 128, smem, s>>>(tmA, tmB, tmB2 ? *tmB2 : tmB, a);
     return finish_launch();
 }
 
@@ -595,9 +716,17 @@ extern "C" int sis3d_pack_conv_weight_tc_x3(const float *w, int cout, int cin, i
     return finish_launch();
 }
 
+extern "C" int sis3d_pack_conv_weight_tc_h3(const float *w, int cout, int cin, int ks, uint16_t *w_h3, void *stream) {
+    if (!w || !w_h3 || cout <= 0 || cin <= 0 || (ks != 1 && ks != 2 && ks != 3)) return SIS3D_EINVAL;
+    const int taps = ks * ks * ks;
+    const int64_t total = (int64_t)cout * taps * cin;
+    pack_conv_weight_tc_h3_kernel<<<(int)imin64(cdiv64(total, 256), 148 * 8), 256, 0, (cudaStream_t)stream>>>(w, cout, cin, taps, (__half *)w_h3);
+    return finish_launch();
+}
+
 static int conv3d_k3_tc_impl(const float *in, const float *w_tc, const float *bias, const float *residual, int res_ld,
                              int res_coff, float *out, int out_ld, int out_coff, int X, int Y, int Z, int cin, int cout,
-                             int ks, const int32_t *tiles, int n_tiles, int act, void *stream, bool x3) {
+                             int ks, const int32_t *tiles, int n_tiles, int act, void *stream, int x3) {
     if (!in || !w_tc || !out || X <= 0 || Y <= 0 || Z <= 0 || (ks != 1 && ks != 2 && ks != 3)) return SIS3D_EINVAL;
     if (ks == 2 && (tiles || X < 2 || Y < 2 || Z < 2)) return SIS3D_EINVAL;
     if (x3 && tiles) return SIS3D_EUNSUPPORTED;  // the ragged mask stage does not need the compensated product
@@ -610,8 +739,13 @@ static int conv3d_k3_tc_impl(const float *in, const float *w_tc, const float *bi
     EncodeTiledFn enc = get_encode();
     if (!enc) return SIS3D_EUNSUPPORTED;
     const int BN = cout >= 128 ? 128 : cout;
-    const int kc = x3 ? 16 : TC_KC;                   // x3: 64-byte K rows (SWIZZLE_64B) so hi + lo tiles fit the same smem
-    const CUtensorMapSwizzle sw = x3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    // x3 = 1 (TF32 split): 64-byte K rows (SWIZZLE_64B) so hi + lo tiles fit the same smem; x3 = 2 (fp16 split): 128-byte fp32
+    // activation rows, pre-split fp16 weights in 64-byte rows
+    const int kc = x3 == 1 ? 16 : TC_KC;
+    const CUtensorMapSwizzle sw = x3 == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapSwizzle swb = x3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapDataType dtb = x3 == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const cuuint64_t wb = x3 == 2 ? 2 : 4;  // weight element bytes
     const int sd = ks == 2 ? 2 : 1;                   // ks == 2 is the stride-2, pad-0 conv: X, Y, Z are the INPUT extents
     const int Xo = X / sd, Yo = Y / sd, Zo = Z / sd;  // output extents (floor, as nn.Conv3d)
     CUtensorMap tmA, tmB;
@@ -627,11 +761,11 @@ static int conv3d_k3_tc_impl(const float *in, const float *w_tc, const float *bi
     }
     {
         cuuint64_t dims[2] = {(cuuint64_t)taps * cin, (cuuint64_t)cout * (x3 ? 2 : 1)};  // x3: hi rows, then lo rows
-        cuuint64_t strides[1] = {(cuuint64_t)taps * cin * 4};
+        cuuint64_t strides[1] = {(cuuint64_t)taps * cin * wb};
         cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)BN};
         cuuint32_t estr[2] = {1, 1};
-        if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)w_tc, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        if (enc(&tmB, dtb, 2, (void *)w_tc, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                swb, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return SIS3D_EINVAL;
     }
     TcArgs a;
@@ -642,6 +776,27 @@ static int conv3d_k3_tc_impl(const float *in, const float *w_tc, const float *bi
     if (!tiles) n_tiles = cdiv(Xo, bx) * a.tiles_y * a.tiles_z;
     if (n_tiles <= 0) return SIS3D_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    if (x3 == 2) {
+        if (ks == 3) {
+            switch (BN) {
+                case 32: return launch_tc<32, 3, 4, 128, 2, 0, 2>(tmA, tmB, a, n_tiles, s);
+                case 64: return launch_tc<64, 3, 4, 128, 2, 0, 2>(tmA, tmB, a, n_tiles, s);
+                default: return launch_tc<128, 3, 4, 128, 2, 0, 2>(tmA, tmB, a, n_tiles, s);
+            }
+        }
+        if (ks == 2) {
+            switch (BN) {
+                case 32: return launch_tc<32, 2, 4, 128, 2, 0, 2>(tmA, tmB, a, n_tiles, s);
+                case 64: return launch_tc<64, 2, 4, 128, 2, 0, 2>(tmA, tmB, a, n_tiles, s);
+                default: return launch_tc<128, 2, 4, 128, 2, 0, 2>(tmA, tmB, a, n_tiles, s);
+            }
+        }
+        switch (BN) {
+            case 32: return launch_tc<32, 1, 4, 128, 2, 0, 2>(tmA, tmB, a, n_tiles, s);
+            case 64: return launch_tc<64, 1, 4, 128, 2, 0, 2>(tmA, tmB, a, n_tiles, s);
+            default: return launch_tc<128, 1, 4, 128, 2, 0, 2>(tmA, tmB, a, n_tiles, s);
+        }
+    }
     if (x3) {
         if (ks == 3) {
             switch (BN) {
@@ -688,14 +843,21 @@ extern "C" int sis3d_conv3d_k3_tc(const float *in, const float *w_tc, const floa
                                   int res_coff, float *out, int out_ld, int out_coff, int X, int Y, int Z, int cin, int cout,
                                   int ks, const int32_t *tiles, int n_tiles, int act, void *stream) {
     return conv3d_k3_tc_impl(in, w_tc, bias, residual, res_ld, res_coff, out, out_ld, out_coff, X, Y, Z, cin, cout, ks, tiles,
-                             n_tiles, act, stream, false);
+                             n_tiles, act, stream, 0);
 }
 // error-compensated 3xTF32 (fp32-class accuracy on the tensor cores): w_x3 from sis3d_pack_conv_weight_tc_x3
 extern "C" int sis3d_conv3d_k3_tc_x3(const float *in, const float *w_x3, const float *bias, const float *residual, int res_ld,
                                      int res_coff, float *out, int out_ld, int out_coff, int X, int Y, int Z, int cin, int cout,
                                      int ks, int act, void *stream) {
     return conv3d_k3_tc_impl(in, w_x3, bias, residual, res_ld, res_coff, out, out_ld, out_coff, X, Y, Z, cin, cout, ks, nullptr, 0,
-                             act, stream, true);
+                             act, stream, 1);
+}
+// the same compensation with an fp16 operand split (2.5x the MMA rate): w_h3 from sis3d_pack_conv_weight_tc_h3
+extern "C" int sis3d_conv3d_k3_tc_h3(const float *in, const uint16_t *w_h3, const float *bias, const float *residual, int res_ld,
+                                     int res_coff, float *out, int out_ld, int out_coff, int X, int Y, int Z, int cin, int cout,
+                                     int ks, int act, void *stream) {
+    return conv3d_k3_tc_impl(in, (const float *)w_h3, bias, residual, res_ld, res_coff, out, out_ld, out_coff, X, Y, Z, cin, cout,
+                             ks, nullptr, 0, act, stream, 2);
 }
 
 // ---- bottleneck tail: 3x3x3 conv (cin -> cmid) + ReLU + 1x1 conv (cmid -> cout) + residual + act, one kernel ----------------
@@ -705,7 +867,7 @@ extern "C" int sis3d_conv3d_k3_tc_fused_supported(int cin, int cmid, int cout) {
 static int conv3d_k3_tc_fused_impl(const float *in, const float *w2_tc, const float *bias2, const float *w3_tc,
                                    const float *bias3, const float *residual, int res_ld, int res_coff, float *out,
                                    int out_ld, int out_coff, int X, int Y, int Z, int cin, int cmid, int cout, int act,
-                                   void *stream, bool x3) {
+                                   void *stream, int x3) {
     if (!in || !w2_tc || !w3_tc || !out || X <= 0 || Y <= 0 || Z <= 0) return SIS3D_EINVAL;
     if (!sis3d_conv3d_k3_tc_fused_supported(cin, cmid, cout)) return SIS3D_EUNSUPPORTED;
     if (((uintptr_t)in | (uintptr_t)w2_tc | (uintptr_t)w3_tc | (uintptr_t)out) & 15) return SIS3D_EINVAL;
@@ -713,8 +875,12 @@ static int conv3d_k3_tc_fused_impl(const float *in, const float *w2_tc, const fl
     EncodeTiledFn enc = get_encode();
     if (!enc) return SIS3D_EUNSUPPORTED;
     const int by = 2, bx = 8;
-    const int kc = x3 ? 16 : TC_KC;
-    const CUtensorMapSwizzle sw = x3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const int kc = x3 == 1 ? 16 : TC_KC;
+    const CUtensorMapSwizzle sw = x3 == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapSwizzle swb = x3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapSwizzle swb2 = x3 == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapDataType dtb = x3 == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const cuuint64_t wb = x3 == 2 ? 2 : 4;
     const int halves = x3 ? 2 : 1;  // x3 weight tensors: hi rows, then lo rows
     CUtensorMap tmA, tmB, tmB2;
     cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -728,18 +894,18 @@ static int conv3d_k3_tc_fused_impl(const float *in, const float *w2_tc, const fl
     }
     {
         cuuint64_t dims[2] = {(cuuint64_t)27 * cin, (cuuint64_t)cmid * halves};
-        cuuint64_t strides[1] = {(cuuint64_t)27 * cin * 4};
+        cuuint64_t strides[1] = {(cuuint64_t)27 * cin * wb};
         cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)cmid};
-        if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)w2_tc, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        if (enc(&tmB, dtb, 2, (void *)w2_tc, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                swb, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return SIS3D_EINVAL;
     }
     {
         cuuint64_t dims[2] = {(cuuint64_t)cmid, (cuuint64_t)cout * halves};
-        cuuint64_t strides[1] = {(cuuint64_t)cmid * 4};
+        cuuint64_t strides[1] = {(cuuint64_t)cmid * wb};
         cuuint32_t box[2] = {TC_KC, (cuuint32_t)cout};
-        if (enc(&tmB2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)w3_tc, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        if (enc(&tmB2, dtb, 2, (void *)w3_tc, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                swb2, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return SIS3D_EINVAL;
     }
     TcArgs a;
@@ -751,6 +917,11 @@ static int conv3d_k3_tc_fused_impl(const float *in, const float *w2_tc, const fl
     a.gemm_m = 0; a.gemm_chunks_per_split = 0;
     const int n_tiles = cdiv(X, bx) * a.tiles_y * a.tiles_z;
     cudaStream_t s = (cudaStream_t)stream;
+    if (x3 == 2) {
+        if (cmid == 32 && cout == 32) return launch_tc<32, 3, 4, 128, 2, 32, 2>(tmA, tmB, a, n_tiles, s, &tmB2);
+        if (cmid == 32 && cout == 64) return launch_tc<32, 3, 4, 128, 2, 64, 2>(tmA, tmB, a, n_tiles, s, &tmB2);
+        return launch_tc<64, 3, 4, 128, 2, 128, 2>(tmA, tmB, a, n_tiles, s, &tmB2);
+    }
     if (x3) {
         if (cmid == 32 && cout == 32) return launch_tc<32, 3, 4, 64, 2, 32, 1>(tmA, tmB, a, n_tiles, s, &tmB2);
         if (cmid == 32 && cout == 64) return launch_tc<32, 3, 4, 64, 2, 64, 1>(tmA, tmB, a, n_tiles, s, &tmB2);
@@ -765,14 +936,21 @@ extern "C" int sis3d_conv3d_k3_tc_fused(const float *in, const float *w2_tc, con
                                         int out_ld, int out_coff, int X, int Y, int Z, int cin, int cmid, int cout, int act,
                                         void *stream) {
     return conv3d_k3_tc_fused_impl(in, w2_tc, bias2, w3_tc, bias3, residual, res_ld, res_coff, out, out_ld, out_coff, X, Y, Z, cin,
-                                   cmid, cout, act, stream, false);
+                                   cmid, cout, act, stream, 0);
 }
 extern "C" int sis3d_conv3d_k3_tc_fused_x3(const float *in, const float *w2_x3, const float *bias2, const float *w3_x3,
                                            const float *bias3, const float *residual, int res_ld, int res_coff, float *out,
                                            int out_ld, int out_coff, int X, int Y, int Z, int cin, int cmid, int cout, int act,
                                            void *stream) {
     return conv3d_k3_tc_fused_impl(in, w2_x3, bias2, w3_x3, bias3, residual, res_ld, res_coff, out, out_ld, out_coff, X, Y, Z, cin,
-                                   cmid, cout, act, stream, true);
+                                   cmid, cout, act, stream, 1);
+}
+extern "C" int sis3d_conv3d_k3_tc_fused_h3(const float *in, const uint16_t *w2_h3, const float *bias2, const uint16_t *w3_h3,
+                                           const float *bias3, const float *residual, int res_ld, int res_coff, float *out,
+                                           int out_ld, int out_coff, int X, int Y, int Z, int cin, int cmid, int cout, int act,
+                                           void *stream) {
+    return conv3d_k3_tc_fused_impl(in, (const float *)w2_h3, bias2, (const float *)w3_h3, bias3, residual, res_ld, res_coff, out,
+                                   out_ld, out_coff, X, Y, Z, cin, cmid, cout, act, stream, 2);
 }
 
 // ---- y[M][N] = act(x[M][K] . w[N][K]^T + b): fully connected layer on the tensor cores (TF32), split-K ------------
@@ -787,15 +965,17 @@ extern "C" size_t sis3d_linear_tc_workspace_bytes(int M, int N, int K) {
     return sizeof(float) * (size_t)gemm_tc_splits(M, N, K, 16) * M * N + 16;  // the x3 variant splits K finer: covers both
 }
 static int linear_tc_impl(const float *x, const float *w_nk, const float *bias, float *y, int M, int K, int N, int act,
-                          void *workspace, size_t workspace_bytes, void *stream, bool x3) {
+                          void *workspace, size_t workspace_bytes, void *stream, int x3) {
     if (!x || !w_nk || !y || !workspace || M <= 0) return SIS3D_EINVAL;
     if (!sis3d_linear_tc_supported(K, N)) return SIS3D_EUNSUPPORTED;
     if (((uintptr_t)x | (uintptr_t)w_nk | (uintptr_t)workspace) & 15) return SIS3D_EINVAL;
     EncodeTiledFn enc = get_encode();
     if (!enc) return SIS3D_EUNSUPPORTED;
     const int BN = N >= 128 ? 128 : N;
-    const int kc = x3 ? 16 : TC_KC;
-    const CUtensorMapSwizzle sw = x3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const int kc = x3 == 1 ? 16 : TC_KC;
+    const CUtensorMapSwizzle sw = x3 == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapSwizzle swb = x3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapDataType dtb = x3 == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     int splits = gemm_tc_splits(M, N, K, kc);
     const int chunks = K / kc;
     const int per = cdiv(chunks, splits);
@@ -811,9 +991,10 @@ static int linear_tc_impl(const float *x, const float *w_nk, const float *bias, 
                 sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return SIS3D_EINVAL;
         cuuint64_t dimsb[2] = {(cuuint64_t)K, (cuuint64_t)N * (x3 ? 2 : 1)};
+        cuuint64_t stridesb[1] = {(cuuint64_t)K * (x3 == 2 ? 2 : 4)};
         cuuint32_t boxb[2] = {(cuuint32_t)kc, (cuuint32_t)BN};
-        if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)w_nk, dimsb, strides, boxb, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        if (enc(&tmB, dtb, 2, (void *)w_nk, dimsb, stridesb, boxb, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                swb, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return SIS3D_EINVAL;
     }
     TcArgs a = {};
@@ -821,7 +1002,11 @@ static int linear_tc_impl(const float *x, const float *w_nk, const float *bias, 
     cudaStream_t s = (cudaStream_t)stream;
     const int mt = cdiv(M, TC_BM);
     int rc;
-    if (x3) {
+    if (x3 == 2) {
+        rc = BN == 32 ? launch_tc<32, 0, 4, 128, 2, 0, 2>(tmA, tmB, a, mt, s, nullptr, splits)
+           : BN == 64 ? launch_tc<64, 0, 4, 128, 2, 0, 2>(tmA, tmB, a, mt, s, nullptr, splits)
+                      : launch_tc<128, 0, 4, 128, 2, 0, 2>(tmA, tmB, a, mt, s, nullptr, splits);
+    } else if (x3) {
         rc = BN == 32 ? launch_tc<32, 0, 4, 64, 2, 0, 1>(tmA, tmB, a, mt, s, nullptr, splits)
            : BN == 64 ? launch_tc<64, 0, 4, 64, 2, 0, 1>(tmA, tmB, a, mt, s, nullptr, splits)
                       : launch_tc<128, 0, 4, 64, 2, 0, 1>(tmA, tmB, a, mt, s, nullptr, splits);
@@ -836,12 +1021,16 @@ static int linear_tc_impl(const float *x, const float *w_nk, const float *bias, 
 }
 extern "C" int sis3d_linear_tc(const float *x, const float *w_nk, const float *bias, float *y, int M, int K, int N, int act,
                                void *workspace, size_t workspace_bytes, void *stream) {
-    return linear_tc_impl(x, w_nk, bias, y, M, K, N, act, workspace, workspace_bytes, stream, false);
+    return linear_tc_impl(x, w_nk, bias, y, M, K, N, act, workspace, workspace_bytes, stream, 0);
 }
 // w_x3 = sis3d_pack_conv_weight_tc_x3(w[N][K] viewed as a 1x1 conv): [2][N][K]
 extern "C" int sis3d_linear_tc_x3(const float *x, const float *w_x3, const float *bias, float *y, int M, int K, int N, int act,
                                   void *workspace, size_t workspace_bytes, void *stream) {
-    return linear_tc_impl(x, w_x3, bias, y, M, K, N, act, workspace, workspace_bytes, stream, true);
+    return linear_tc_impl(x, w_x3, bias, y, M, K, N, act, workspace, workspace_bytes, stream, 1);
+}
+extern "C" int sis3d_linear_tc_h3(const float *x, const uint16_t *w_h3, const float *bias, float *y, int M, int K, int N, int act,
+                                  void *workspace, size_t workspace_bytes, void *stream) {
+    return linear_tc_impl(x, (const float *)w_h3, bias, y, M, K, N, act, workspace, workspace_bytes, stream, 2);
 }
 
 // ---- fp16-operand variant (kind::f16): activations and weights stored as fp16, fp32 accumulation in TMEM ----------

@@ -8,6 +8,7 @@
 //
 // IoU arithmetic is pinned with explicit intrinsics to the SASS nvcc emits for the reference's
 // devIoU (Sa = FMUL,FMUL; t = FFMA(wb*hb, lb, Sa); u = t - inter; IEEE div) -- see DESIGN.md.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace sis3d {
@@ -297,6 +298,183 @@ __global__ void rpn_pad_kernel(float *rois, float *scores, int32_t *level_ids, c
     }
 }
 
+
+// ---- RPN stages 3-6 in ONE single-CTA kernel: exact top-K, decode + clip, NMS bitmask, greedy reduce, padded outputs ----
+// (the four-kernel chain above costs ~85 us of pure latency per scene: global round trips between single-CTA kernels and an
+// 8-round radix select; here the candidates are sorted directly in shared memory -- the coarse histogram cut of stage 2
+// leaves a few hundred to a few thousand of them -- and the K x K/64 suppression bitmask never leaves shared memory.)
+// Same keys, same decode arithmetic, same IoU bits and the same greedy order as the separate kernels: identical outputs.
+constexpr int kFusedCandCap = 4096;  // candidates sorted in shared memory; more (a huge tie at the cut) -> multi-kernel path
+constexpr int kFusedMaxK = 512;      // pre-NMS top-N the fused kernel handles (TEST uses 400)
+
+__device__ __forceinline__ void decode_box(const RpnLevels &L, int f, float *box, int &lvl_id) {
+    int lvl, vox, a, x, y, z;
+    decode_flat(L, f, lvl, vox, a, x, y, z);
+    lvl_id = lvl + 1;
+    const float *sz = L.sizes[lvl] + a * 3;
+    const float *d = L.deltas[lvl] + (int64_t)vox * L.deltas_ld[lvl] + a * 6;
+    const float st = (float)L.feat_stride;
+    const float pos[3] = {st * x, st * y, st * z};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        // anchor (lo, hi) = pos -/+ size/2 are exact in fp32; bbox_transform_inv with one rounding per op
+        const float lo = pos[k] - 0.5f * sz[k], hi = pos[k] + 0.5f * sz[k];
+        const float w = __fsub_rn(hi, lo);
+        const float ctr = __fadd_rn(lo, __fmul_rn(0.5f, w));
+        const float pc = __fadd_rn(__fmul_rn(__ldg(d + k), w), ctr);
+        const float pw = __fmul_rn(expf(__ldg(d + 3 + k)), w);
+        const float hw = __fmul_rn(0.5f, pw);
+        const float dim = (float)L.scene[k];
+        box[k] = fminf(fmaxf(__fsub_rn(pc, hw), 0.f), dim);
+        box[3 + k] = fminf(fmaxf(__fadd_rn(pc, hw), 0.f), dim);
+    }
+}
+
+__global__ void __launch_bounds__(1024) rpn_select_nms_kernel(const RpnLevels L, const unsigned long long *cand, const int *cand_count,
+                                                              int K, int cb, float thresh, int post_top_n, float *rois, float *scores,
+                                                              int32_t *level_ids, int32_t *num_out, int32_t *order_out) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(s_raw);           // [kFusedCandCap]
+    unsigned long long *s_mask = s_keys + kFusedCandCap;                                    // [K][cb]
+    unsigned long long *s_remv = s_mask + (size_t)K * cb;                                   // [cb]
+    float *s_box = reinterpret_cast<float *>(s_remv + cb);                                  // [K][6]
+    float *s_score = s_box + (size_t)K * 6;                                                 // [K]
+    int32_t *s_lvl = reinterpret_cast<int32_t *>(s_score + K);                              // [K]
+    __shared__ unsigned long long s_kept, s_prefix;
+    __shared__ int s_nkept, s_hist[256], s_need, s_fill;
+    const int t = threadIdx.x, nt = blockDim.x;
+    const int Mtot = *cand_count;
+    int M = Mtot;
+    const int Keff = min(K, Mtot);
+    for (int j = t; j < cb; j += nt) s_remv[j] = 0;
+    if (t == 0) { s_nkept = 0; s_prefix = 0; s_need = Keff; s_fill = 0; }
+    __syncthreads();
+    if (Mtot > kFusedCandCap) {
+        // thousands of scores share the histogram bin of the K-th best: radix-select the exact K-th key over the global list
+        // first (8 passes), then only the K keys at or above it enter shared memory
+        for (int r = 0; r < 8; ++r) {
+            for (int i = t; i < 256; i += nt) s_hist[i] = 0;
+            __syncthreads();
+            const unsigned long long prefix = s_prefix;
+            const int shift = 56 - 8 * r;
+            for (int i = t; i < Mtot; i += nt) {
+                const unsigned long long k = cand[i];
+                if (r == 0 || (k >> (shift + 8)) == prefix) atomicAdd(&s_hist[(int)((k >> shift) & 255ULL)], 1);
+            }
+            __syncthreads();
+            if (t == 0) {
+                int need = s_need, d = 255;
+                for (; d > 0; --d) { if (s_hist[d] >= need) break; need -= s_hist[d]; }
+                s_need = need;
+                s_prefix = (prefix << 8) | (unsigned long long)d;
+            }
+            __syncthreads();
+        }
+        const unsigned long long T = s_prefix;
+        for (int i = t; i < Mtot; i += nt) {
+            const unsigned long long k = cand[i];
+            if (k >= T) { const int p = atomicAdd(&s_fill, 1); if (p < kFusedCandCap) s_keys[p] = k; }
+        }
+        __syncthreads();
+        M = min(s_fill, kFusedCandCap);  // == K (keys are unique)
+    }
+    int P = 2;
+    while (P < M) P <<= 1;  // sort size: every candidate, padded with zero keys (zero sorts last; real keys are non-zero)
+    for (int i = t; i < P; i += nt)
+        if (Mtot <= kFusedCandCap) s_keys[i] = i < M ? cand[i] : 0ULL;
+        else if (i >= M) s_keys[i] = 0ULL;
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1)  // bitonic sort, descending (keys are unique: score bits | ~flat index)
+        for (int strd = size >> 1; strd > 0; strd >>= 1) {
+            for (int i = t; i < P; i += nt) {
+                const int j = i ^ strd;
+                if (j > i) {
+                    const unsigned long long a = s_keys[i], b = s_keys[j];
+                    const bool desc = ((i & size) == 0);
+                    if (desc ? (a < b) : (a > b)) { s_keys[i] = b; s_keys[j] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    // decode + clip the K best (rows >= Keff: zero boxes that are never emitted)
+    for (int i = t; i < K; i += nt) {
+        float box[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float score = 0.f;
+        int lvl_id = 0, f = -1;
+        if (i < Keff) {
+            const unsigned long long key = s_keys[i];
+            f = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFULL));
+            score = __uint_as_float((unsigned)(key >> 32));
+            decode_box(L, f, box, lvl_id);
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s_box[i * 6 + k] = box[k];
+        s_score[i] = score;
+        s_lvl[i] = lvl_id;
+        if (order_out) order_out[i] = f;
+    }
+    __syncthreads();
+    // suppression bitmask, upper triangle: word (i, c) bit j <=> IoU(box i, box 64c + j) > thresh for 64c + j > i
+    for (int wd = t; wd < Keff * cb; wd += nt) {
+        const int i = wd / cb, c = wd - i * cb;
+        unsigned long long bits = 0;
+        if (c >= (i >> 6)) {
+            const float *a = s_box + i * 6;
+            const float Sa = box_volume_p1(a);
+            const int jn = min(Keff - c * 64, 64);
+            for (int j = (c == (i >> 6)) ? (i & 63) + 1 : 0; j < jn; ++j)
+                if (iou3d_ref(a, Sa, s_box + (c * 64 + j) * 6) > thresh) bits |= 1ULL << j;
+        }
+        s_mask[wd] = bits;
+    }
+    __syncthreads();
+    // greedy reduce (nms_reduce_kernel's order): in-block chain resolved serially, suppression ORed into later column blocks
+    for (int rb = 0; rb * 64 < Keff; ++rb) {
+        const int rows = min(Keff - rb * 64, 64);
+        if (t == 0) {
+            unsigned long long cur = s_remv[rb], kept = 0;
+            for (int i = 0; i < rows; ++i)
+                if (!((cur >> i) & 1ULL)) { kept |= 1ULL << i; cur |= s_mask[(size_t)(rb * 64 + i) * cb + rb]; }
+            s_kept = kept;
+        }
+        __syncthreads();
+        const unsigned long long kept = s_kept;
+        if (t < rows && ((kept >> t) & 1ULL)) {
+            const int pos = s_nkept + __popcll(kept & ((1ULL << t) - 1ULL));
+            const int i = rb * 64 + t;
+            if (pos < post_top_n) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) rois[pos * 6 + k] = s_box[i * 6 + k];
+                scores[pos] = s_score[i];
+                level_ids[pos] = s_lvl[i];
+            }
+        }
+        const int ncols = cb - rb - 1;
+        for (int w = t; w < ncols * 64; w += nt) {
+            const int i = w & 63, j = rb + 1 + (w >> 6);
+            if (i < rows && ((kept >> i) & 1ULL)) {
+                const unsigned long long m = s_mask[(size_t)(rb * 64 + i) * cb + j];
+                if (m) atomicOr(&s_remv[j], m);
+            }
+        }
+        __syncthreads();
+        if (t == 0) s_nkept += __popcll(kept);
+        __syncthreads();
+    }
+    const int n = min(s_nkept, post_top_n);
+    if (t == 0) *num_out = n;
+    for (int i = n + t; i < post_top_n; i += nt) {  // zero the padded tail (downstream kernels always process post_top_n rows)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) rois[i * 6 + k] = 0.f;
+        scores[i] = 0.f;
+        level_ids[i] = 0;
+    }
+}
+
+static inline size_t fused_smem_bytes(int K, int cb) {
+    return sizeof(unsigned long long) * ((size_t)kFusedCandCap + (size_t)K * cb + cb) + sizeof(float) * 7 * (size_t)K + sizeof(int32_t) * K + 64;
+}
+
 static inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 struct RpnWs {  // workspace carve-up (all 8-byte aligned)
@@ -378,6 +556,21 @@ extern "C" int sis3d_rpn_proposals(const sis3d_rpn_level *lv, int n_levels, int 
     const int blocks = min(cdiv(total, 256), kNumSMs * 4);
     rpn_score_kernel<<<blocks, 256, 0, s>>>(L, w.keys, w.hist);
     rpn_candidates_kernel<<<blocks, 256, 0, s>>>(w.keys, total, w.hist, pre_top_n, w.cand, w.cand_count);
+    const int cb = cdiv(pre_top_n, 64);
+    if (pre_top_n <= kFusedMaxK && !getenv("SIS3D_RPN_UNFUSED")) {
+        // stages 3-6 in one kernel (sorts the candidates in shared memory; if thousands of scores share the histogram bin of
+        // the K-th best it first radix-selects the exact K-th key over the global list, so the result is exact in every case)
+        static bool attr = false;
+        const size_t smem = fused_smem_bytes(pre_top_n, cb);
+        if (!attr) {
+            if (cudaFuncSetAttribute(rpn_select_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_bytes(kFusedMaxK, cdiv(kFusedMaxK, 64))) != cudaSuccess)
+                return SIS3D_ELAUNCH;
+            attr = true;
+        }
+        rpn_select_nms_kernel<<<1, 1024, smem, s>>>(L, w.cand, w.cand_count, pre_top_n, cb, nms_thresh, post_top_n, rois, scores,
+                                                     level_ids, num_out, debug_order);
+        return finish_launch(3);
+    }
     const int Kp2 = next_pow2(pre_top_n);
     if ((size_t)Kp2 * 8 > 48 * 1024)
         cudaFuncSetAttribute(rpn_topk_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Kp2 * 8);
@@ -386,7 +579,6 @@ extern "C" int sis3d_rpn_proposals(const sis3d_rpn_level *lv, int n_levels, int 
     // NMS over the (zero padded) pre_top_n rows is wrong when fewer than pre_top_n candidates exist:
     // padded all-zero boxes would suppress each other only, but must not be emitted -> the reduce is
     // bounded by n_sorted on the device.
-    const int cb = cdiv(pre_top_n, 64);
     nms_mask_kernel<<<dim3(cb, cb), 64, 0, s>>>(w.sorted_boxes, pre_top_n, nms_thresh, w.mask, cb);
     NmsGather g = {w.sorted_boxes, w.sorted_scores, w.sorted_levels, rois, scores, level_ids, post_top_n};
     nms_reduce_kernel<<<1, 256, cb * 8, s>>>(w.mask, pre_top_n, w.n_sorted, cb, nullptr, num_out, g);

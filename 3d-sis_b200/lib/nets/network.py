@@ -113,7 +113,8 @@ class Network(nn.Module):
         self._packed_tc = {}
         self._packed_h = {}
         self._packed_x3 = {}
-        # conv math (see set_conv_math).  Default 'exact': error-compensated 3xTF32 (fp32-class accuracy, tcgen05) in the
+        self._packed_h3 = {}
+        # conv math (see set_conv_math).  Default 'exact': error-compensated split products (fp32-class accuracy, tcgen05) in the
         # static stage -- everything that decides an integer output: proposal order, NMS keep list, class argmax, crop
         # bounds -- and fp16-stored operands in the ragged mask stage, whose outputs carry the 1e-3 tolerance.
         self.set_conv_math(os.environ.get("SIS3D_CONV_MATH", str(cfg.get("CONV_MATH", "exact"))).lower())
@@ -261,8 +262,9 @@ class Network(nn.Module):
         return v
 
     MATH_MODES = {  # mode -> (static-stage conv math, mask-stage conv math)
-        "exact": ("tf32x3", "fp16"),   # default: integer outputs equal the fp32 path, masks within 1e-3
-        "tf32x3": ("tf32x3", "tf32"),
+        "exact": ("f16x3", "fp16"),    # default: integer outputs equal the fp32 path, masks within 1e-3
+        "f16x3": ("f16x3", "tf32"),    # error-compensated fp16 split (3 kind::f16 MMAs per product, fp32-class accuracy)
+        "tf32x3": ("tf32x3", "tf32"),  # the same compensation with a TF32 split (3 kind::tf32 MMAs: 2.5x slower tensor pipe)
         "mixed": ("tf32", "fp16"),     # fastest; detections equal the reference only up to near-tied scores
         "tf32": ("tf32", "tf32"),
         "fp16": ("fp16", "fp16"),
@@ -270,8 +272,8 @@ class Network(nn.Module):
     }
 
     def set_conv_math(self, mode):
-        """'exact' (3xTF32 static stage + fp16-operand mask stage) | 'tf32x3' | 'mixed' (TF32 + fp16) | 'tf32' | 'fp16' |
-        'fp32' (CUDA-core path)."""
+        """'exact' (error-compensated fp16-split static stage + fp16-operand mask stage) | 'f16x3' | 'tf32x3' | 'mixed' (TF32 +
+        fp16) | 'tf32' | 'fp16' | 'fp32' (CUDA-core path)."""
         if mode not in self.MATH_MODES:
             raise S.Sis3dError(f"unknown conv math {mode!r} ({' | '.join(self.MATH_MODES)})")
         self.__dict__["_math"], self.__dict__["_mask_math"] = self.MATH_MODES[mode]
@@ -290,7 +292,7 @@ class Network(nn.Module):
         self._pack_dirty = False
         if v == self._packed_version:
             return
-        self._packed, self._packed_tc, self._packed_h, self._packed_x3 = {}, {}, {}, {}
+        self._packed, self._packed_tc, self._packed_h, self._packed_x3, self._packed_h3 = {}, {}, {}, {}, {}
         params = dict(self.named_parameters())
         self.__dict__["_enet"] = None
         if self.__dict__.get("_enet_names"):
@@ -318,6 +320,9 @@ class Network(nn.Module):
                 wx3 = torch.empty(2 * cout, ks ** 3 * cin, dtype=torch.float32, device=w.device)
                 S.check(S.lib.sis3d_pack_conv_weight_tc_x3(S.ptr(w), cout, cin, ks, S.ptr(wx3), S.stream()), "pack_x3")
                 self._packed_x3[base] = wx3
+                wh3 = torch.empty(2 * cout, ks ** 3 * cin, dtype=torch.float16, device=w.device)
+                S.check(S.lib.sis3d_pack_conv_weight_tc_h3(S.ptr(w), cout, cin, ks, S.ptr(wh3), S.stream()), "pack_h3")
+                self._packed_h3[base] = wh3
                 if ks != 2 and (cin % 64 == 0 or cin == 32):
                     w16 = torch.empty(cout, ks ** 3 * cin, dtype=torch.float16, device=w.device)
                     S.check(S.lib.sis3d_pack_conv_weight_tc_f16(S.ptr(w), cout, cin, ks, S.ptr(w16), S.stream()), "pack_f16")
@@ -326,6 +331,9 @@ class Network(nn.Module):
                 wx3 = torch.empty(2 * cout, cin, dtype=torch.float32, device=w.device)  # nn.Linear [N][K] = a 1x1 conv
                 S.check(S.lib.sis3d_pack_conv_weight_tc_x3(S.ptr(w), cout, cin, 1, S.ptr(wx3), S.stream()), "pack_x3")
                 self._packed_x3[base] = wx3
+                wh3 = torch.empty(2 * cout, cin, dtype=torch.float16, device=w.device)
+                S.check(S.lib.sis3d_pack_conv_weight_tc_h3(S.ptr(w), cout, cin, 1, S.ptr(wh3), S.stream()), "pack_h3")
+                self._packed_h3[base] = wh3
         for lvl in (1, 2, 3):  # both RPN heads of a level as ONE 1x1 conv: [2A | 6A] output channels, zero-padded to a
             # tensor-core friendly width (32/64/128k) so the merged head runs on the tcgen05 kernel as well
             c, b = f"rpn_cls_score_net_level{lvl}.0", f"rpn_bbox_pred_net_level{lvl}"
@@ -348,6 +356,9 @@ class Network(nn.Module):
                     wx3 = torch.empty(2 * cpad, cin, dtype=torch.float32, device=w.device)
                     S.check(S.lib.sis3d_pack_conv_weight_tc_x3(S.ptr(wp), cpad, cin, 1, S.ptr(wx3), S.stream()), "pack_x3")
                     self._packed_x3[f"rpn_heads_level{lvl}"] = wx3
+                    wh3 = torch.empty(2 * cpad, cin, dtype=torch.float16, device=w.device)
+                    S.check(S.lib.sis3d_pack_conv_weight_tc_h3(S.ptr(wp), cpad, cin, 1, S.ptr(wh3), S.stream()), "pack_h3")
+                    self._packed_h3[f"rpn_heads_level{lvl}"] = wh3
                     w16 = torch.empty(cpad, cin, dtype=torch.float16, device=w.device)
                     S.check(S.lib.sis3d_pack_conv_weight_tc_f16(S.ptr(wp), cpad, cin, 1, S.ptr(w16), S.stream()), "pack_f16")
                     self._packed_h[f"rpn_heads_level{lvl}"] = w16
@@ -435,10 +446,12 @@ class Network(nn.Module):
             raise S.Sis3dError(f"{name}: this layer needs the fp32 activation but only the fp16 twin was produced")
         if out.t is None and h_ptr is None:
             out.t = torch.empty(*out_dims, cout, dtype=torch.float32, device=dev)
-        if self._math == "tf32x3" and tc_ok and name in self._packed_x3 and out.t is not None and h_ptr is None:
-            tok = self._rec(f"conv_tc_x3[{name}]")
-            S.check(S.lib.sis3d_conv3d_k3_tc_x3(S.ptr(x.t), S.ptr(self._packed_x3[name]), S.ptr(bias), *res_args,
-                                                S.ptr(out.t), out.ld, out.coff, *x.dims, cin, cout, ks, act, S.stream()),
+        if self._math in ("tf32x3", "f16x3") and tc_ok and name in self._packed_x3 and out.t is not None and h_ptr is None:
+            h3 = self._math == "f16x3"
+            tok = self._rec(f"conv_tc_{'h3' if h3 else 'x3'}[{name}]")
+            fn = S.lib.sis3d_conv3d_k3_tc_h3 if h3 else S.lib.sis3d_conv3d_k3_tc_x3
+            S.check(fn(S.ptr(x.t), S.ptr((self._packed_h3 if h3 else self._packed_x3)[name]), S.ptr(bias), *res_args,
+                       S.ptr(out.t), out.ld, out.coff, *x.dims, cin, cout, ks, act, S.stream()),
                     f"conv3d_k3_tc_x3[{name}]")
             self._rec_end(tok)
             return out
@@ -468,12 +481,14 @@ class Network(nn.Module):
         packed, bias, cout, cin, _ = self._packed[name]
         M = x.shape[0]
         y = torch.empty(M, cout, dtype=torch.float32, device=x.device)
-        if self._math == "tf32x3" and name in self._packed_x3:
+        if self._math in ("tf32x3", "f16x3") and name in self._packed_x3:
+            h3 = self._math == "f16x3"
             nbytes = int(S.lib.sis3d_linear_tc_workspace_bytes(M, cout, cin))
             ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-            tok = self._rec(f"linear_tc_x3[{name}]")
-            S.check(S.lib.sis3d_linear_tc_x3(S.ptr(x), S.ptr(self._packed_x3[name]), S.ptr(bias), S.ptr(y), M, cin, cout, act,
-                                             S.ptr(ws), C.c_size_t(nbytes), S.stream()), f"linear_tc_x3[{name}]")
+            tok = self._rec(f"linear_tc_{'h3' if h3 else 'x3'}[{name}]")
+            fn = S.lib.sis3d_linear_tc_h3 if h3 else S.lib.sis3d_linear_tc_x3
+            S.check(fn(S.ptr(x), S.ptr((self._packed_h3 if h3 else self._packed_x3)[name]), S.ptr(bias), S.ptr(y), M, cin, cout, act,
+                       S.ptr(ws), C.c_size_t(nbytes), S.stream()), f"linear_tc_x3[{name}]")
             self._rec_end(tok)
             return y
         if self._math == "tf32" and cin >= 1024 and S.lib.sis3d_linear_tc_supported(cin, cout):
@@ -499,17 +514,19 @@ class Network(nn.Module):
         is a dense tensor, for the next block's first conv)."""
         y = self._conv(x, name + ".conv1", act=1, want32=False, want16=True)
         n2, n3 = name + ".conv2", name + ".conv3"
-        x3 = self._math == "tf32x3"
-        wt = self._packed_x3 if x3 else self._packed_tc
-        if self._math in ("tf32", "tf32x3") and self._fuse_bneck and n2 in wt and n3 in wt and y.t is not None:
+        x3 = self._math in ("tf32x3", "f16x3")
+        h3 = self._math == "f16x3"
+        wt = self._packed_h3 if h3 else (self._packed_x3 if x3 else self._packed_tc)
+        if self._math in ("tf32", "tf32x3", "f16x3") and self._fuse_bneck and n2 in wt and n3 in wt and y.t is not None:
             _, _, cmid, cin, _ = self._packed[n2]
             cout = self._packed[n3][2]
             if y.ld == y.C and y.coff == 0 and S.lib.sis3d_conv3d_k3_tc_fused_supported(cin, cmid, cout):
                 # conv2 + conv3 (+x, ReLU) in one tcgen05 kernel: the cmid-wide activation never leaves the SM
                 if out is None:
                     out = Act(torch.empty(*y.dims, cout, dtype=torch.float32, device=y.t.device), y.dims, cout)
-                tok = self._rec(f"conv_tc_fused{'_x3' if x3 else ''}[{name}]")
-                fn = S.lib.sis3d_conv3d_k3_tc_fused_x3 if x3 else S.lib.sis3d_conv3d_k3_tc_fused
+                tok = self._rec(f"conv_tc_fused{'_h3' if h3 else '_x3' if x3 else ''}[{name}]")
+                fn = (S.lib.sis3d_conv3d_k3_tc_fused_h3 if h3 else S.lib.sis3d_conv3d_k3_tc_fused_x3 if x3
+                      else S.lib.sis3d_conv3d_k3_tc_fused)
                 S.check(fn(S.ptr(y.t), S.ptr(wt[n2]), S.ptr(self._packed[n2][1]),
                            S.ptr(wt[n3]), S.ptr(self._packed[n3][1]), S.ptr(x.t), x.ld, x.coff, S.ptr(out.t), out.ld, out.coff, *y.dims, cin,
                            cmid, cout, 1, S.stream()), f"conv3d_k3_tc_fused[{name}]")

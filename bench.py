@@ -471,14 +471,16 @@ def main():
     rb = torch.zeros(256, device=dev)
     ro = torch.empty(24, 12, 24, 256, device=dev)
     sh = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    x3 = net._math == "tf32x3"
-    wp = torch.empty(512 if x3 else 256, 27 * 128, device=dev)
-    S.check((S.lib.sis3d_pack_conv_weight_tc_x3 if x3 else S.lib.sis3d_pack_conv_weight_tc)(S.ptr(rw), 256, 128, 3, S.ptr(wp), sh), "pack")
+    h3 = net._math == "f16x3"
+    x3 = net._math in ("tf32x3", "f16x3")
+    wp = torch.empty(512 if x3 else 256, 27 * 128, device=dev, dtype=torch.float16 if h3 else torch.float32)
+    S.check((S.lib.sis3d_pack_conv_weight_tc_h3 if h3 else S.lib.sis3d_pack_conv_weight_tc_x3 if x3
+             else S.lib.sis3d_pack_conv_weight_tc)(S.ptr(rw), 256, 128, 3, S.ptr(wp), sh), "pack")
 
     def rpn_conv():
         if x3:
-            S.check(S.lib.sis3d_conv3d_k3_tc_x3(S.ptr(rx), S.ptr(wp), S.ptr(rb), None, 0, 0, S.ptr(ro), 256, 0, 24, 12, 24, 128, 256,
-                                                3, 1, sh), "rpn conv x3")
+            S.check((S.lib.sis3d_conv3d_k3_tc_h3 if h3 else S.lib.sis3d_conv3d_k3_tc_x3)(
+                S.ptr(rx), S.ptr(wp), S.ptr(rb), None, 0, 0, S.ptr(ro), 256, 0, 24, 12, 24, 128, 256, 3, 1, sh), "rpn conv x3")
         else:
             S.check(S.lib.sis3d_conv3d_k3_tc(S.ptr(rx), S.ptr(wp), S.ptr(rb), None, 0, 0, S.ptr(ro), 256, 0, 24, 12, 24, 128, 256, 3,
                                              None, 0, 1, sh), "rpn conv")
@@ -493,6 +495,7 @@ def main():
     rpn_ms = ke0.elapsed_time(ke1) / 40
     pk = peaks()
     tf32_peak = measure_tf32_peak(dev)
+    mma_peak = pk["bf16_burst"] if (h3 or net._math == "fp16") else tf32_peak  # the tensor-pipe rate this kernel's MMAs run at
     traffic = profile_traffic()
     value = total_scenes / (ms_dev / 1e3)
     e2e_v = total_scenes / (ms_e2e / 1e3)
@@ -506,16 +509,20 @@ def main():
     issued = tf * (3 if x3 else 1)
     tensor_roof = {
         "bound": "tensor",
-        "kernel": f"conv3d_k3_tc_kernel<128,3{',X3' if x3 else ''}> (rpn_net_level1/2: 3x3x3, 128 -> 256 ch, 24x12x24; "
-                  + ("error-compensated 3xTF32: three tcgen05 MMAs per algorithmic product" if x3 else "TF32 in") + ", fp32 accumulate)",
-        "achieved": tf, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tf / tf32_peak,
-        "peak_note": "cuBLAS TF32 GEMM 8192^3 measured in this run (burst, best of 10): the kernel is timed in isolation",
+        "kernel": f"conv3d_k3_tc_kernel<128,3{',X3=2' if h3 else ',X3=1' if x3 else ''}> (rpn_net_level1/2: 3x3x3, 128 -> 256 ch, 24x12x24; "
+                  + ("error-compensated fp16 split: three tcgen05 kind::f16 MMAs per algorithmic product" if h3 else
+                     "error-compensated 3xTF32: three tcgen05 MMAs per algorithmic product" if x3 else "TF32 in") + ", fp32 accumulate)",
+        "achieved": tf, "peak": mma_peak, "unit": "TFLOP/s", "frac": tf / mma_peak,
+        "peak_note": ("measured bf16/fp16 GEMM burst peak of MEASURED_PEAKS.json (the kernel's MMAs are kind::f16)" if mma_peak != tf32_peak
+                      else "cuBLAS TF32 GEMM 8192^3 measured in this run (burst, best of 10)") + "; the kernel is timed in isolation; "
+                     "`achieved` counts ALGORITHMIC flops, `issued_mma_tflops` the 3x MMA work of the compensated product",
         "flops_per_launch": 12.231e9, "ms_per_launch": rpn_ms, "launches_timed": 40,
-        "issued_mma_tflops": issued, "issued_frac": issued / tf32_peak,
+        "issued_mma_tflops": issued, "issued_frac": issued / mma_peak,
         "traffic": traffic.get("rpn_kernel_dram_bytes_per_launch") if traffic else None,
         "traffic_note": "dram__bytes_read+write per launch, ncu --set full capture of this build (profiles/r2_traffic.json)"
                         if traffic else "null: no ncu capture of this exact build (sources hash) is committed"}
-    dtype = {"exact": "3xTF32 error-compensated (static-stage convs) / f16 operands (mask-stage convs) on tcgen05, fp32 accumulate, + f32",
+    dtype = {"exact": "f16 hi/lo split, error-compensated 3-MMA products (static-stage convs: fp32-class accuracy) / f16 operands (mask-stage convs) on tcgen05, fp32 accumulate, + f32",
+             "f16x3": "f16 hi/lo split, error-compensated 3-MMA products (static stage) / tf32 (mask stage) on tcgen05, fp32 accumulate, + f32",
              "tf32x3": "3xTF32 error-compensated (static stage) / tf32 (mask stage) on tcgen05, fp32 accumulate, + f32",
              "tf32": "tf32 (convs on tcgen05, fp32 accumulate) + f32",
              "mixed": "tf32 (static-stage convs) / f16 operands (mask-stage convs) on tcgen05, fp32 accumulate, + f32",

@@ -235,7 +235,12 @@ def reference_forward(net, cfg, data, views):
         helper = ProjectionHelper(cfg.INTRINSIC, cfg.PROJ_DEPTH_MIN, cfg.PROJ_DEPTH_MAX, cfg.DEPTH_SHAPE,
                                   blobs["data"].shape[-3:], cfg.VOXEL_SIZE)
         w2g = torch.from_numpy(views["world2grid"])
-        maps = [helper.compute_projection(torch.from_numpy(d), torch.from_numpy(c), w2g)
+        vol = int(np.prod(blobs["data"].shape[-3:]))
+        if vol > cfg.MAX_VOLUME or len(views["depths"]) > cfg.MAX_IMAGE:  # trainval.py:800-801: projection on the CPU
+            dev = lambda t: t
+        else:                                                              # :802-803 (`.cuda()` is a no-op under the CPU shims)
+            dev = lambda t: t.cuda()
+        maps = [helper.compute_projection(dev(torch.from_numpy(d)), dev(torch.from_numpy(c)), dev(w2g))
                 for d, c in zip(views["depths"], views["poses"])]
         killing = [i for i, m in enumerate(maps) if m is None]
         real = [m for m in maps if m is not None]

@@ -74,6 +74,51 @@ def test_rpn_proposals_emulated_vs_oracle(oracle, host_S, dims, seed):
     assert not rois[n:].any()
 
 
+def test_rpn_fused_tail_huge_tie_and_unfused_chain_agree(oracle, host_S, monkeypatch):
+    """The single-CTA fused tail (sort in shared memory, NMS bitmask in shared memory) against the four-kernel chain, and its
+    exact fallback when more candidates share the histogram bin of the K-th best than fit in shared memory: with every
+    foreground probability EQUAL all ~7.5k inside anchors are candidates, and the stable order (lower flat index first) decides."""
+    from lib.layer_utils.proposal_layer import rpn_proposals
+    from lib.utils.config import cfg_from_file, cfg_reset
+    cfg_reset()
+    cfg_from_file(os.path.join(ROOT, "3d-sis_b200", "experiments", "cfgs", "ScanNet", "rpn_class_mask_5.yml"))
+    ocfg = oracle.make_cfg("scannet")
+    rng = np.random.default_rng(9)
+    dims = (20, 10, 18)
+    scene = tuple(4 * d for d in dims)
+    for tie in (True, False):
+        levels, olevels = [], []
+        for A, tab in ((3, "scannet14_3.txt"), (11, "scannet14_11.txt")):
+            n = dims[0] * dims[1] * dims[2]
+            prob = np.full((n, A), 0.625, np.float32) if tie else rng.uniform(0, 1, (n, A)).astype(np.float32)
+            dl = (rng.standard_normal((n, 6 * A)) * 0.2).astype(np.float32)
+            sizes = oracle.read_anchor_table(tab)
+            levels.append(dict(cls=torch.from_numpy(prob), deltas=torch.from_numpy(dl), sizes=torch.tensor(sizes, dtype=torch.float32),
+                               grid=dims, A=A, cls_mode=1))
+            olevels.append((torch.from_numpy(prob).reshape(-1), torch.from_numpy(dl).view(-1, 6), oracle.generate_anchors(dims, sizes, 4)))
+        want = oracle.proposal_layer(ocfg, olevels, scene, fma_mode=1)
+        inside = np.concatenate([oracle.inside_mask(l[2], scene) for l in olevels])
+        if tie:
+            assert inside.sum() > 4096  # more candidates than the fused kernel sorts in shared memory
+        outs = {}
+        for unfused in (False, True):
+            if unfused:
+                monkeypatch.setenv("SIS3D_RPN_UNFUSED", "1")
+            else:
+                monkeypatch.delenv("SIS3D_RPN_UNFUSED", raising=False)
+            rois, scores, lvl, num, order = rpn_proposals(levels, scene, "TEST", want_order=True)
+            n = int(num.item())
+            outs[unfused] = (rois.clone(), scores.clone(), lvl.clone(), n, order.clone())
+            assert np.array_equal(order.numpy()[:len(want["order"])], np.nonzero(inside)[0][want["order"]])
+            assert n == len(want["rois"])
+            np.testing.assert_allclose(rois[:n].numpy(), want["rois"].numpy(), atol=1e-4, rtol=1e-5)
+            assert np.array_equal(lvl[:n].numpy(), want["level_inds"].numpy().astype(np.int32))
+            assert not rois[n:].any()
+        a, b = outs[False], outs[True]
+        assert a[3] == b[3] and all(torch.equal(x, y) for x, y in zip(a[:3], b[:3])) and torch.equal(a[4], b[4])
+    monkeypatch.delenv("SIS3D_RPN_UNFUSED", raising=False)
+
+
 def test_roi_pool_emulated_vs_oracle(oracle, emu):
     rng = np.random.default_rng(1)
     Cn, dims = 8, (12, 6, 11)
