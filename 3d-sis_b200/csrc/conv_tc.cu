@@ -20,6 +20,7 @@
 // Reference call sites: Bottleneck.conv2 (lib/nets/backbones.py:21), geometry2.0 (:216),
 // rpn_net_level{1,2} (lib/nets/network.py:40,45), MaskBackbone.geometry.{2,4,6,8} (backbones.py:243-249).
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_fp16.h>
 #include "common.cuh"
 
@@ -40,6 +41,7 @@ struct TcArgs {
     int gemm_m, gemm_chunks_per_split;  // KS == 0 (plain GEMM y = x W^T, split-K over blockIdx.z)
     __half *out16;                      // optional fp16 twin of the output (same geometry as `out`); `out` may be null
     const float *bias_mid;              // N2 > 0: bias of the 3x3x3 conv (added before the inner ReLU), or null
+    int n_tiles;                        // bricks of this launch (the grid may be padded to a multiple of the cluster size)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -76,6 +78,27 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// cluster variants (CL = 2: two CTAs = two bricks of the same N tile share every weight tile: each CTA fetches half of them and
+// multicasts to both -> half the weight bytes per SM over the L2->SM crossbar, which bounds the wide / weight-heavy layers)
+__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 // start>>4 [0,14) | LBO=1 [16,30) | SBO=1024B>>4 [32,46) | version=1 [46,48) | layout=SWIZZLE_128B(2) [61,64)
 // ROWB = 128: SWIZZLE_128B (layout 2, 8-row atom = 1024 B);  ROWB = 64: SWIZZLE_64B (layout 4, 8-row atom = 512 B)
@@ -185,20 +208,22 @@ struct TcStages { static constexpr int value = BN >= 128 ? 4 : 3; };
 // stage count per kernel flavour: the 3x3x3 stages are 3x bigger (slab + three weight tiles)
 // X3 (error-compensated 3xTF32, 64-byte K rows): every stage also holds the low parts of A and B; BN = 32 keeps three
 // stages (96 KB, two CTAs per SM), BN = 64 two (88 KB, two CTAs per SM), BN = 128 three (204 KB)
-// X3 = 2 (fp16 split, 128-byte fp32 source rows): a stage = fp32 landing slab + fp16 hi/lo slabs + fp16 hi/lo weight tiles;
-// BN = 32: two stages (104 KB: two CTAs share an SM, one's prologue/epilogue under the other's main loop; the 64-wide fused tail's
-// W3 tiles push that 1.5 KB over the limit, so it runs one CTA with four stages), BN = 64: three, BN = 128: two (176 KB)
+// X3 = 2 (fp16 split, 128-byte fp32 source rows): a stage = the slab (fp32 as it lands, split IN PLACE into fp16 hi / lo tiles of
+// half the size each) + fp16 hi/lo weight tiles.  3x3x3: BN = 32: three stages of 32 KB (two CTAs share an SM: one's prologue /
+// epilogue runs under the other's main loop), BN = 64: four of 44 KB, BN = 128: three of 68 KB (two stages left the TMA round
+// trip exposed: 49 us -> the MMA/feed bound); 1x1 / 2x2x2 / GEMM: four.
 template <int BN, int KS, int ROWB, int X3 = 0, int N2 = 0>
 struct TcStagesOf {
     static constexpr int value =
-        X3 == 2 ? (KS == 3 ? (BN == 32 ? (N2 == 64 ? 4 : 2) : BN == 64 ? 3 : 2) : (BN >= 128 ? 4 : 3))
+        X3 == 2 ? (KS == 3 ? (BN == 64 ? 4 : 3) : 4)
                 : (KS == 3 ? (X3 ? (BN == 64 ? 2 : 3) : (BN >= 128 ? 3 : 2)) : TcStages<BN>::value);
 };  // narrow 3x3x3 layers: 2 stages so 2-3 CTAs share an SM
 template <int BN, int KS, int ROWB, int BY, int N2 = 0, int X3 = 0>
 constexpr size_t tc_smem_bytes() {
     // bytes of one weight row in shared memory: ROWB, or 64 (32 fp16 channels) in the fp16-split mode
-    return (size_t)TcStagesOf<BN, KS, ROWB, X3, N2>::value * (X3 ? 2 : 1) *
-               ((KS == 3 ? (16 / BY + 2) * BY * TC_BZ : TC_BM) * ROWB + (KS == 3 ? 3 : 1) * BN * (X3 == 2 ? 64 : ROWB)) +
+    return (size_t)TcStagesOf<BN, KS, ROWB, X3, N2>::value *
+               ((X3 == 1 ? 2 : 1) * (KS == 3 ? (16 / BY + 2) * BY * TC_BZ : TC_BM) * ROWB +
+                (X3 == 1 ? 2 : 1) * (KS == 3 ? 3 : 1) * BN * (X3 == 2 ? 128 : ROWB)) +
            (size_t)(X3 == 1 ? 2 : 1) * N2 * 128 * (BN / 32) + 1024 + 256;
 }
 constexpr int tc_tmem_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
@@ -224,13 +249,14 @@ constexpr int tc_tmem_cols(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 12
 // X3 = 2 (EB = 4, ROWB = 128): the same compensation with an fp16 split (split_f16 above): the fp32 slab lands in a staging
 // buffer, warps 2-3 write its hi and (scaled) lo parts as two fp16 K-major SWIZZLE_64B tiles, the weights are pre-split fp16
 // tiles, and the three products are kind::f16 MMAs -- same 22 significand bits, 2.5x the MMA rate, half as many stages.
-template <int BN, int KS, int EB = 4, int ROWB = 128, int BY = 2, int N2 = 0, int X3 = 0>
+template <int BN, int KS, int EB = 4, int ROWB = 128, int BY = 2, int N2 = 0, int X3 = 0, int CL = 1>
 __global__ void __launch_bounds__(X3 == 2 ? 256 : 128, (X3 == 2 && BN == 32) ? 2 : 1) conv3d_k3_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
                                                               const __grid_constant__ CUtensorMap tmB2, const TcArgs a) {
     static_assert(N2 == 0 || (KS == 3 && EB == 4), "conv3 fusion: TF32 3x3x3 kernels only");
     static_assert(X3 == 0 || EB == 4, "3xTF32 splits fp32-stored operands");
     static_assert(X3 != 2 || ROWB == 128, "the fp16 split reads 128-byte fp32 rows and writes 64-byte fp16 rows");
+    static_assert(CL == 1 || (CL == 2 && KS == 3), "weight-tile multicast: pairs of 3x3x3 bricks");
     constexpr bool XH = X3 == 2;             // fp16 split
     // threads: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2.. = operand splitters (X3), every warp = epilogue.  The fp16
     // split re-lays the slab out (fp32 128-byte rows -> two fp16 64-byte-row tiles), ~4 ALU ops per element: six splitter warps
@@ -246,17 +272,22 @@ __global__ void __launch_bounds__(X3 == 2 ? 256 : 128, (X3 == 2 && BN == 32) ? 2
     constexpr int XT = KS == 3 ? 3 : 1;      // x-taps per stage
     constexpr int A_ROWS = KS == 3 ? (TC_BX + 2) * TC_BY * TC_BZ : TC_BM;
     constexpr int A_BYTES = A_ROWS * ROWB;
-    constexpr int B_BYTES = BN * OPB;
+    // weight tiles: X3 = 2 keeps the hi and lo halves of a 32-channel K slice side by side in ONE 128-byte row (one TMA row
+    // request instead of two 64-byte ones: the per-SM TMA path moves ~one row per 2.7 cycles whatever its length, and the
+    // 64-byte rows made the weight tiles 3/4 of a stage's requests), SWIZZLE_128B; hi = first 64 bytes, lo = last 64
+    constexpr int BROW = XH ? 128 : OPB;
+    constexpr int NBT = XT * (X3 == 1 ? 2 : 1);  // weight tiles per stage
+    constexpr int B_BYTES = BN * BROW;
     // stage layout: X3 = 0: [A | B x XT];  X3 = 1: [A_hi (in place) | A_lo | B_hi x XT | B_lo x XT];
-    //               X3 = 2: [A fp32 (staging) | A_hi fp16 | A_lo fp16 | B_hi x XT | B_lo x XT]  (fp16 tiles: half of A_BYTES each)
-    constexpr int B_OFF = (X3 ? 2 : 1) * A_BYTES;
-    constexpr int STAGE_BYTES = (X3 ? 2 : 1) * (A_BYTES + XT * B_BYTES);
+    //               X3 = 2: [A: fp32 as landed -> split in place into A_hi fp16 | A_lo fp16 (half of A_BYTES each) | B_hi x XT | B_lo x XT]
+    constexpr int B_OFF = (X3 == 1 ? 2 : 1) * A_BYTES;
+    constexpr int STAGE_BYTES = B_OFF + NBT * B_BYTES;
     constexpr int TC_STAGES = TcStagesOf<BN, KS, ROWB, X3, N2>::value;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B needs 1024 B alignment
     // W3 as BN/32 K slices of [N2 rows][32 ch] (X3: hi slices, then lo slices; fp16 split: 64-byte rows)
-    constexpr int B2_SLICE = N2 * (XH ? 64 : 128);
-    constexpr int B2_BYTES = (X3 ? 2 : 1) * B2_SLICE * (BN / 32);
+    constexpr int B2_SLICE = N2 * 128;  // fp16 split: [hi 64 B | lo 64 B] per row
+    constexpr int B2_BYTES = (X3 == 1 ? 2 : 1) * B2_SLICE * (BN / 32);
     // X3 accumulators: the tensor core adds into its fp32 accumulator with truncation, a bias that grows with the length of the
     // accumulation chain -- invisible next to TF32 operand rounding, but the dominant error of the compensated product.  So the
     // hi.hi terms rotate over THREE accumulators (stage it -> it % 3: chains a third as long, summed with round-to-nearest adds in
@@ -273,7 +304,7 @@ __global__ void __launch_bounds__(X3 == 2 ? 256 : 128, (X3 == 2 && BN == 32) ? 2
 
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); mbar_init(conv_done + i, NSPLIT); }
+        for (int i = 0; i < TC_STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, CL); mbar_init(conv_done + i, NSPLIT); }
         mbar_init(acc_ready, 1);
         mbar_init(b2_full, 1);
         mbar_init(acc2_ready, 1);
@@ -288,14 +319,21 @@ __global__ void __launch_bounds__(X3 == 2 ? 256 : 128, (X3 == 2 && BN == 32) ? 2
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    uint32_t crank = 0;
+    if constexpr (CL > 1) {
+        // both CTAs' barriers are initialised before either multicasts into the other's shared memory / arrives on its barriers
+        cluster_sync_all();
+        crank = cluster_ctarank();
+    }
 
     // ---- which brick
     int x0 = 0, y0 = 0, z0 = 0, x1 = 0, y1 = 0, z1 = 0;
     if constexpr (KS == 0) {
         // GEMM mode: rows instead of bricks (x0 = first row, set below)
     } else if (a.tiles) {
-        const int32_t *t = a.tiles + (size_t)blockIdx.x * 8;
+        const int32_t *t = a.tiles + (size_t)min((int)blockIdx.x, a.n_tiles - 1) * 8;
         x0 = t[0]; y0 = t[1]; z0 = t[2]; x1 = t[3]; y1 = t[4]; z1 = t[5];
+        if ((int)blockIdx.x >= a.n_tiles) x1 = y1 = z1 = 0;  // cluster padding: runs the pipeline (its peer needs it), stores nothing
     } else {
         const int tz = blockIdx.x % a.tiles_z, ty = (blockIdx.x / a.tiles_z) % a.tiles_y, tx = blockIdx.x / (a.tiles_z * a.tiles_y);
         x0 = tx * TC_BX; y0 = ty * TC_BY; z0 = tz * TC_BZ;
@@ -316,41 +354,46 @@ __global__ void __launch_bounds__(X3 == 2 ? 256 : 128, (X3 == 2 && BN == 32) ? 2
         if constexpr (N2 > 0) {
             mbar_expect_tx(b2_full, B2_BYTES);
 #pragma unroll
-            for (int h = 0; h < (X3 ? 2 : 1); ++h)  // X3: rows [N2, 2 N2) of the split W3 are the low parts
+            for (int h = 0; h < (X3 == 1 ? 2 : 1); ++h)  // X3 = 1: rows [N2, 2 N2) of the split W3 are the low parts
 #pragma unroll
-                for (int kc = 0; kc < BN / 32; ++kc)
-                    tma_load_2d(smem_b2 + (h * (BN / 32) + kc) * B2_SLICE, &tmB2, b2_full, kc * 32, h * N2);
+                for (int kc = 0; kc < BN / 32; ++kc)  // X3 = 2: one 64-half row per K slice = [32 hi | 32 lo]
+                    tma_load_2d(smem_b2 + (h * (BN / 32) + kc) * B2_SLICE, &tmB2, b2_full, kc * (XH ? 64 : 32), h * N2);
         }
         for (int it = 0; it < total; ++it) {
             const int s = it % TC_STAGES;
             const uint32_t ph = (it / TC_STAGES) & 1;
             mbar_wait(empty + s, ph ^ 1);
-            mbar_expect_tx(full + s, STAGE_BYTES - (X3 ? A_BYTES : 0));  // X3: the split tiles are written by warps 2-3, not by TMA
+            mbar_expect_tx(full + s, STAGE_BYTES - (X3 == 1 ? A_BYTES : 0));  // X3 = 1: A_lo is written by the splitter warps, not by TMA
             const int tap = it / kchunks, kc = it - tap * kchunks;
             uint8_t *sa = smem + s * STAGE_BYTES;
             if constexpr (KS == 0) {
                 tma_load_2d(sa, &tmA, full + s, (chunk0 + it) * KC, x0);
-                tma_load_2d(sa + B_OFF, &tmB, full + s, (chunk0 + it) * KC, n0);
-                if constexpr (X3) tma_load_2d(sa + B_OFF + B_BYTES, &tmB, full + s, (chunk0 + it) * KC, a.cout + n0);
+                tma_load_2d(sa + B_OFF, &tmB, full + s, (chunk0 + it) * KC * (XH ? 2 : 1), n0);
+                if constexpr (X3 == 1) tma_load_2d(sa + B_OFF + B_BYTES, &tmB, full + s, (chunk0 + it) * KC, a.cout + n0);
             } else if constexpr (KS == 1) {
                 tma_load_4d(sa, &tmA, full + s, kc * KC, z0, y0, x0);
-                tma_load_2d(sa + B_OFF, &tmB, full + s, kc * KC, n0);
-                if constexpr (X3) tma_load_2d(sa + B_OFF + B_BYTES, &tmB, full + s, kc * KC, a.cout + n0);
+                tma_load_2d(sa + B_OFF, &tmB, full + s, kc * KC * (XH ? 2 : 1), n0);
+                if constexpr (X3 == 1) tma_load_2d(sa + B_OFF + B_BYTES, &tmB, full + s, kc * KC, a.cout + n0);
             } else if constexpr (KS == 2) {
                 // 2x2x2 / stride 2: the tensor map traverses the input with element strides {1,2,2,2}, so the box that starts
                 // at input voxel (2 x0 + dx, 2 y0 + dy, 2 z0 + dz) lands as the 128 output rows of this brick for tap (dx,dy,dz)
                 const int dx = tap >> 2, dy = (tap >> 1) & 1, dz = tap & 1;
                 tma_load_4d(sa, &tmA, full + s, kc * KC, 2 * z0 + dz, 2 * y0 + dy, 2 * x0 + dx);
-                tma_load_2d(sa + B_OFF, &tmB, full + s, tap * a.cin + kc * KC, n0);
-                if constexpr (X3) tma_load_2d(sa + B_OFF + B_BYTES, &tmB, full + s, tap * a.cin + kc * KC, a.cout + n0);
+                tma_load_2d(sa + B_OFF, &tmB, full + s, (tap * a.cin + kc * KC) * (XH ? 2 : 1), n0);
+                if constexpr (X3 == 1) tma_load_2d(sa + B_OFF + B_BYTES, &tmB, full + s, tap * a.cin + kc * KC, a.cout + n0);
             } else {
                 const int dy = tap / 3, dz = tap % 3;  // tap = (dy, dz) pair; the slab covers x0-1 .. x0+8
                 tma_load_4d(sa, &tmA, full + s, kc * KC, z0 + dz - 1, y0 + dy - 1, x0 - 1);
 #pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {  // weight rows k = ((dx*3+dy)*3+dz)*C_in + c
-                    tma_load_2d(sa + B_OFF + dx * B_BYTES, &tmB, full + s, ((dx * 3 + dy) * 3 + dz) * a.cin + kc * KC, n0);
-                    if constexpr (X3)
-                        tma_load_2d(sa + B_OFF + (3 + dx) * B_BYTES, &tmB, full + s, ((dx * 3 + dy) * 3 + dz) * a.cin + kc * KC, a.cout + n0);
+                for (int j = 0; j < NBT; ++j) {  // weight tiles: x-taps 0..2 (X3 = 1: hi tiles, then the low parts' tiles)
+                    const int dx = j % 3, row0 = (j >= 3 ? a.cout : 0) + n0;
+                    // weight columns k = ((dx*3+dy)*3+dz)*C_in + c  (X3 = 2: two halves per k -- [32 hi | 32 lo] per K slice)
+                    const int kcol = (((dx * 3 + dy) * 3 + dz) * a.cin + kc * KC) * (XH ? 2 : 1);
+                    if constexpr (CL == 1) {
+                        tma_load_2d(sa + B_OFF + j * B_BYTES, &tmB, full + s, kcol, row0);
+                    } else if ((uint32_t)(j % CL) == crank) {  // this CTA's share of the pair's weight tiles, delivered to both
+                        tma_load_2d_mc(sa + B_OFF + j * B_BYTES, &tmB, full + s, kcol, row0, (uint16_t)((1u << CL) - 1u));
+                    }
                 }
             }
         }
@@ -366,8 +409,8 @@ __global__ void __launch_bounds__(X3 == 2 ? 256 : 128, (X3 == 2 && BN == 32) ? 2
             mbar_wait(X3 ? conv_done + s : full + s, ph);  // X3: the split (which itself waited for the TMA) is done
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + B_OFF;
-            // operand tiles: X3 = 1: hi at sa (in place), lo at sa + A_BYTES; X3 = 2: fp16 hi at sa + A_BYTES, lo half an A_BYTES on
-            const uint32_t a_hi = sa + (XH ? A_BYTES : 0), a_lo = sa + A_BYTES + (XH ? A_BYTES / 2 : 0);
+            // operand tiles: X3 = 1: hi at sa (in place), lo at sa + A_BYTES; X3 = 2: fp16 hi at sa (in place), lo half an A_BYTES on
+            const uint32_t a_hi = sa, a_lo = sa + (XH ? A_BYTES / 2 : A_BYTES);
 #pragma unroll
             for (int dx = 0; dx < XT; ++dx) {
                 // x-tap dx: A rows start 16 rows (= two 8-row swizzle atoms) further into the slab
@@ -377,7 +420,8 @@ __global__ void __launch_bounds__(X3 == 2 ? 256 : 128, (X3 == 2 && BN == 32) ? 2
                     const uint32_t acc = (it | dx | k) ? 1u : 0u;
                     if constexpr (X3) {  // cross terms A_lo.B_hi + A_hi.B_lo -> accumulator 3; A_hi.B_hi -> accumulator it % 3
                         const uint64_t ah = umma_desc<OPB>(ax + k * 32), al = umma_desc<OPB>(al_x + k * 32);
-                        const uint64_t bh = umma_desc<OPB>(bx + k * 32), bl = umma_desc<OPB>(bx + XT * B_BYTES + k * 32);
+                        const uint64_t bh = umma_desc<BROW>(bx + k * 32);
+                        const uint64_t bl = XH ? umma_desc<BROW>(bx + 64 + k * 32) : umma_desc<BROW>(bx + XT * B_BYTES + k * 32);
                         const uint32_t dm = tmem_base + (uint32_t)((it % 3) * BN), acc_m = ((it >= 3) | dx | k) ? 1u : 0u;
                         if constexpr (XH) {
                             umma_f16(tmem_base + 3 * BN, al, bh, idesc, acc);
@@ -392,7 +436,9 @@ __global__ void __launch_bounds__(X3 == 2 ? 256 : 128, (X3 == 2 && BN == 32) ? 2
                     else umma_f16(tmem_base, umma_desc<ROWB>(ax + k * 32), umma_desc<ROWB>(bx + k * 32), idesc, acc);
                 }
             }
-            umma_commit(empty + s);  // frees the smem slot once these MMAs retire
+            // frees the smem slot once these MMAs retire (cluster: in BOTH CTAs -- the peer's producer multicasts into this slot too)
+            if constexpr (CL == 1) umma_commit(empty + s);
+            else umma_commit_mc(empty + s, (uint16_t)((1u << CL) - 1u));
         }
         umma_commit(acc_ready);
     } else if (X3 && warp >= 2) {
@@ -404,19 +450,32 @@ __global__ void __launch_bounds__(X3 == 2 ? 256 : 128, (X3 == 2 && BN == 32) ? 2
             uint8_t *st = smem + s * STAGE_BYTES;
             if constexpr (XH) {
                 // fp32 slab (128-byte rows, SWIZZLE_128B: 16-byte chunk j of row r at r*128 + ((j ^ (r & 7)) << 4)) ->
-                // fp16 hi / lo tiles (64-byte rows, SWIZZLE_64B: chunk q of row r at r*64 + ((q ^ ((r >> 1) & 3)) << 4));
-                // one work item = 8 channels of one row = source chunks 2q, 2q+1 -> destination chunk q
-                uint8_t *hi = st + A_BYTES, *lo = st + A_BYTES + A_BYTES / 2;
-#pragma unroll 2
-                for (int i = t; i < A_ROWS * 4; i += NSPLIT) {
-                    const int r = i >> 2, q = i & 3;
-                    const float4 v0 = *reinterpret_cast<const float4 *>(st + r * 128 + (((2 * q) ^ (r & 7)) << 4));
-                    const float4 v1 = *reinterpret_cast<const float4 *>(st + r * 128 + (((2 * q + 1) ^ (r & 7)) << 4));
-                    uint4 h, l;
-                    split_f16x8(v0, v1, h, l);
-                    const int d = r * 64 + ((q ^ ((r >> 1) & 3)) << 4);
-                    *reinterpret_cast<uint4 *>(hi + d) = h;
-                    *reinterpret_cast<uint4 *>(lo + d) = l;
+                // fp16 hi / lo tiles (64-byte rows, SWIZZLE_64B: chunk q of row r at r*64 + ((q ^ ((r >> 1) & 3)) << 4)), IN PLACE:
+                // hi takes the first half of the slab's bytes, lo the second.  One work item = 8 channels of one row = source
+                // chunks 2q, 2q+1 -> destination chunk q.  Every splitter thread converts its items into registers, the splitter
+                // warps meet at a named barrier (all of the fp32 data has been read), then the fp16 tiles are stored.
+                constexpr int ITEMS = (A_ROWS * 4 + NSPLIT - 1) / NSPLIT;
+                uint4 h[ITEMS], l[ITEMS];
+#pragma unroll
+                for (int u = 0; u < ITEMS; ++u) {
+                    const int i = t + u * NSPLIT;
+                    if (i < A_ROWS * 4) {
+                        const int r = i >> 2, q = i & 3;
+                        const float4 v0 = *reinterpret_cast<const float4 *>(st + r * 128 + (((2 * q) ^ (r & 7)) << 4));
+                        const float4 v1 = *reinterpret_cast<const float4 *>(st + r * 128 + (((2 * q + 1) ^ (r & 7)) << 4));
+                        split_f16x8(v0, v1, h[u], l[u]);
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(NSPLIT) : "memory");
+#pragma unroll
+                for (int u = 0; u < ITEMS; ++u) {
+                    const int i = t + u * NSPLIT;
+                    if (i < A_ROWS * 4) {
+                        const int r = i >> 2, q = i & 3;
+                        const int d = r * 64 + ((q ^ ((r >> 1) & 3)) << 4);
+                        *reinterpret_cast<uint4 *>(st + d) = h[u];
+                        *reinterpret_cast<uint4 *>(st + A_BYTES / 2 + d) = l[u];
+                    }
                 }
             } else {
                 // slab -> hi (in place) + lo (second buffer): the split is elementwise, so the swizzled layout is untouched
@@ -524,10 +583,11 @@ __global__ void __launch_bounds__(X3 == 2 ? 256 : 128, (X3 == 2 && BN == 32) ? 2
             for (int kc = 0; kc < BN / 32; ++kc)
 #pragma unroll
                 for (int k = 0; k < OP2 / 32; ++k) {
-                    const uint64_t ah = umma_desc<OP2>(sa2 + kc * A2_SLICE + k * 32), bh = umma_desc<OP2>(sb2 + kc * B2_SLICE + k * 32);
+                    const uint64_t ah = umma_desc<OP2>(sa2 + kc * A2_SLICE + k * 32), bh = umma_desc<128>(sb2 + kc * B2_SLICE + k * 32);
                     if constexpr (X3) {
                         const uint64_t al = umma_desc<OP2>(sa2 + A2_BYTES + kc * A2_SLICE + k * 32);
-                        const uint64_t bl = umma_desc<OP2>(sb2 + (BN / 32 + kc) * B2_SLICE + k * 32);
+                        const uint64_t bl = XH ? umma_desc<128>(sb2 + kc * B2_SLICE + 64 + k * 32)
+                                               : umma_desc<128>(sb2 + (BN / 32 + kc) * B2_SLICE + k * 32);
                         if constexpr (XH) {
                             umma_f16(tmem_base + 4 * BN + N2, al, bh, idesc2, (kc | k) ? 1u : 0u);
                             umma_f16(tmem_base + 4 * BN + N2, ah, bl, idesc2, 1u);
@@ -587,6 +647,7 @@ __global__ void __launch_bounds__(X3 == 2 ? 256 : 128, (X3 == 2 && BN == 32) ? 2
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if constexpr (CL > 1) cluster_sync_all();  // no CTA exits while its peer may still multicast into it / arrive on its barriers
 }
 
 __global__ void gemm_splitk_reduce_kernel(const float *part, int splits, int64_t split_stride, const float *bias, float *y, int M,
@@ -625,7 +686,8 @@ __global__ void pack_conv_weight_tc_x3_kernel(const float *w, int cout, int cin,
     }
 }
 
-// fp16-split weights: rows [0, cout) = fp16(w), rows [cout, 2 cout) = fp16((w - fp16(w)) * 2048); same k order
+// fp16-split weights [cout][K/32][64]: per 32-channel K slice (k = tap*cin + c) 32 hi halves = fp16(w), then 32 lo halves =
+// fp16((w - fp16(w)) * 2048) -- one 128-byte row per (output channel, K slice), so a TMA box row carries both parts
 __global__ void pack_conv_weight_tc_h3_kernel(const float *w, int cout, int cin, int taps, __half *out) {
     const int64_t total = (int64_t)cout * taps * cin;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -634,8 +696,10 @@ __global__ void pack_conv_weight_tc_h3_kernel(const float *w, int cout, int cin,
         const int n = (int)(i / ((int64_t)cin * taps));
         __half hi, lo;
         split_f16(w[((int64_t)n * cin + c) * taps + tap], hi, lo);
-        out[i] = hi;
-        out[total + i] = lo;
+        const int64_t k = (int64_t)tap * cin + c;
+        const int64_t o = ((int64_t)n * taps * cin + (k & ~(int64_t)31)) * 2 + (k & 31);
+        out[o] = hi;
+        out[o + 32] = lo;
     }
 }
 
@@ -653,18 +717,32 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-template <int BN, int KS, int EB = 4, int ROWB = 128, int BY = 2, int N2 = 0, int X3 = 0>
-static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcArgs &a, int n_tiles, cudaStream_t s,
+template <int BN, int KS, int EB = 4, int ROWB = 128, int BY = 2, int N2 = 0, int X3 = 0, int CL = 1>
+static int launch_tc(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcArgs &a_in, int n_tiles, cudaStream_t s,
                      const CUtensorMap *tmB2 = nullptr, int grid_z = 1) {
     const size_t smem = tc_smem_bytes<BN, KS, ROWB, BY, N2, X3>();
+    auto kern = conv3d_k3_tc_kernel<BN, KS, EB, ROWB, BY, N2, X3, CL>;
     static bool attr_done = false;
     if (!attr_done) {
-        if (cudaFuncSetAttribute(conv3d_k3_tc_kernel<BN, KS, EB, ROWB, BY, N2, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return SIS3D_ELAUNCH;
         attr_done = true;
     }
-    dim3 grid(n_tiles, N2 > 0 ? 1 : a.cout / BN, grid_z);
-    conv3d_k3_tc_kernel<BN, KS, EB, ROWB, BY, N2, X3><<<grid, X3 == 2 ? 256 : 128, smem, s>>>(tmA, tmB, tmB2 ? *tmB2 : tmB, a);
+    TcArgs a = a_in;
+    a.n_tiles = n_tiles;
+    const int threads = X3 == 2 ? 256 : 128;
+    dim3 grid((n_tiles + CL - 1) / CL * CL, N2 > 0 ? 1 : a.cout / BN, grid_z);
+    if constexpr (CL == 1) {
+        kern<<<grid, threads, smem, s>>>(tmA, tmB, tmB2 ? *tmB2 : tmB, a);
+    } else {  // thread-block cluster of CL CTAs along x (pairs of bricks)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmB2 ? *tmB2 : tmB, a) != cudaSuccess) return SIS3D_ELAUNCH;
+    }
     return finish_launch();
 }
 
@@ -724,6 +802,14 @@ extern "C" int sis3d_pack_conv_weight_tc_h3(const float *w, int cout, int cin, i
     return finish_launch();
 }
 
+// SIS3D_CLUSTER=1 turns the 2-CTA weight-tile multicast ON (validated: all parity tests pass with it; measured on B200 it does not
+// pay -- 2414 vs 2529 scenes/s, rpn_net 44.5 vs 44.0 us -- because the bound is the rate at which an SM RECEIVES TMA rows, which
+// multicast does not change; kept as an A/B switch)
+static bool use_cluster() {
+    static const bool on = getenv("SIS3D_CLUSTER") != nullptr && getenv("SIS3D_CLUSTER")[0] == '1';
+    return on;
+}
+
 static int conv3d_k3_tc_impl(const float *in, const float *w_tc, const float *bias, const float *residual, int res_ld,
                              int res_coff, float *out, int out_ld, int out_coff, int X, int Y, int Z, int cin, int cout,
                              int ks, const int32_t *tiles, int n_tiles, int act, void *stream, int x3) {
@@ -743,7 +829,7 @@ static int conv3d_k3_tc_impl(const float *in, const float *w_tc, const float *bi
     // activation rows, pre-split fp16 weights in 64-byte rows
     const int kc = x3 == 1 ? 16 : TC_KC;
     const CUtensorMapSwizzle sw = x3 == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
-    const CUtensorMapSwizzle swb = x3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapSwizzle swb = x3 == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
     const CUtensorMapDataType dtb = x3 == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     const cuuint64_t wb = x3 == 2 ? 2 : 4;  // weight element bytes
     const int sd = ks == 2 ? 2 : 1;                   // ks == 2 is the stride-2, pad-0 conv: X, Y, Z are the INPUT extents
@@ -760,9 +846,10 @@ static int conv3d_k3_tc_impl(const float *in, const float *w_tc, const float *bi
             return SIS3D_EINVAL;
     }
     {
-        cuuint64_t dims[2] = {(cuuint64_t)taps * cin, (cuuint64_t)cout * (x3 ? 2 : 1)};  // x3: hi rows, then lo rows
-        cuuint64_t strides[1] = {(cuuint64_t)taps * cin * wb};
-        cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)BN};
+        // x3 = 1: hi rows, then lo rows; x3 = 2: [32 hi | 32 lo] halves per 32-channel K slice in one 128-byte row
+        cuuint64_t dims[2] = {(cuuint64_t)taps * cin * (x3 == 2 ? 2 : 1), (cuuint64_t)cout * (x3 == 1 ? 2 : 1)};
+        cuuint64_t strides[1] = {dims[0] * wb};
+        cuuint32_t box[2] = {(cuuint32_t)(x3 == 2 ? 64 : kc), (cuuint32_t)BN};
         cuuint32_t estr[2] = {1, 1};
         if (enc(&tmB, dtb, 2, (void *)w_tc, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 swb, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -781,7 +868,8 @@ static int conv3d_k3_tc_impl(const float *in, const float *w_tc, const float *bi
             switch (BN) {
                 case 32: return launch_tc<32, 3, 4, 128, 2, 0, 2>(tmA, tmB, a, n_tiles, s);
                 case 64: return launch_tc<64, 3, 4, 128, 2, 0, 2>(tmA, tmB, a, n_tiles, s);
-                default: return launch_tc<128, 3, 4, 128, 2, 0, 2>(tmA, tmB, a, n_tiles, s);
+                default: return use_cluster() ? launch_tc<128, 3, 4, 128, 2, 0, 2, 2>(tmA, tmB, a, n_tiles, s)
+                                              : launch_tc<128, 3, 4, 128, 2, 0, 2>(tmA, tmB, a, n_tiles, s);
             }
         }
         if (ks == 2) {
@@ -819,7 +907,8 @@ static int conv3d_k3_tc_impl(const float *in, const float *w_tc, const float *bi
         }
     }
     if (ks == 3) {
-        if (by == 4) return launch_tc<64, 3, 4, 128, 4>(tmA, tmB, a, n_tiles, s);
+        if (by == 4) return use_cluster() ? launch_tc<64, 3, 4, 128, 4, 0, 0, 2>(tmA, tmB, a, n_tiles, s)
+                                          : launch_tc<64, 3, 4, 128, 4>(tmA, tmB, a, n_tiles, s);
         switch (BN) {
             case 32: return launch_tc<32, 3>(tmA, tmB, a, n_tiles, s);
             case 64: return launch_tc<64, 3>(tmA, tmB, a, n_tiles, s);
@@ -877,11 +966,12 @@ static int conv3d_k3_tc_fused_impl(const float *in, const float *w2_tc, const fl
     const int by = 2, bx = 8;
     const int kc = x3 == 1 ? 16 : TC_KC;
     const CUtensorMapSwizzle sw = x3 == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
-    const CUtensorMapSwizzle swb = x3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
-    const CUtensorMapSwizzle swb2 = x3 == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapSwizzle swb = x3 == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapSwizzle swb2 = CU_TENSOR_MAP_SWIZZLE_128B;
     const CUtensorMapDataType dtb = x3 == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     const cuuint64_t wb = x3 == 2 ? 2 : 4;
-    const int halves = x3 ? 2 : 1;  // x3 weight tensors: hi rows, then lo rows
+    const int halves = x3 == 1 ? 2 : 1;  // x3 = 1 weight tensors: hi rows, then lo rows
+    const int kmul = x3 == 2 ? 2 : 1;    // x3 = 2: [32 hi | 32 lo] halves per K slice in one row
     CUtensorMap tmA, tmB, tmB2;
     cuuint32_t estr[4] = {1, 1, 1, 1};
     {
@@ -893,17 +983,17 @@ static int conv3d_k3_tc_fused_impl(const float *in, const float *w2_tc, const fl
             return SIS3D_EINVAL;
     }
     {
-        cuuint64_t dims[2] = {(cuuint64_t)27 * cin, (cuuint64_t)cmid * halves};
-        cuuint64_t strides[1] = {(cuuint64_t)27 * cin * wb};
-        cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)cmid};
+        cuuint64_t dims[2] = {(cuuint64_t)27 * cin * kmul, (cuuint64_t)cmid * halves};
+        cuuint64_t strides[1] = {dims[0] * wb};
+        cuuint32_t box[2] = {(cuuint32_t)(x3 == 2 ? 64 : kc), (cuuint32_t)cmid};
         if (enc(&tmB, dtb, 2, (void *)w2_tc, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 swb, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return SIS3D_EINVAL;
     }
     {
-        cuuint64_t dims[2] = {(cuuint64_t)cmid, (cuuint64_t)cout * halves};
-        cuuint64_t strides[1] = {(cuuint64_t)cmid * wb};
-        cuuint32_t box[2] = {TC_KC, (cuuint32_t)cout};
+        cuuint64_t dims[2] = {(cuuint64_t)cmid * kmul, (cuuint64_t)cout * halves};
+        cuuint64_t strides[1] = {dims[0] * wb};
+        cuuint32_t box[2] = {(cuuint32_t)(TC_KC * kmul), (cuuint32_t)cout};
         if (enc(&tmB2, dtb, 2, (void *)w3_tc, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 swb2, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return SIS3D_EINVAL;
@@ -920,7 +1010,8 @@ static int conv3d_k3_tc_fused_impl(const float *in, const float *w2_tc, const fl
     if (x3 == 2) {
         if (cmid == 32 && cout == 32) return launch_tc<32, 3, 4, 128, 2, 32, 2>(tmA, tmB, a, n_tiles, s, &tmB2);
         if (cmid == 32 && cout == 64) return launch_tc<32, 3, 4, 128, 2, 64, 2>(tmA, tmB, a, n_tiles, s, &tmB2);
-        return launch_tc<64, 3, 4, 128, 2, 128, 2>(tmA, tmB, a, n_tiles, s, &tmB2);
+        return use_cluster() ? launch_tc<64, 3, 4, 128, 2, 128, 2, 2>(tmA, tmB, a, n_tiles, s, &tmB2)
+                             : launch_tc<64, 3, 4, 128, 2, 128, 2>(tmA, tmB, a, n_tiles, s, &tmB2);
     }
     if (x3) {
         if (cmid == 32 && cout == 32) return launch_tc<32, 3, 4, 64, 2, 32, 1>(tmA, tmB, a, n_tiles, s, &tmB2);
@@ -974,7 +1065,7 @@ static int linear_tc_impl(const float *x, const float *w_nk, const float *bias, 
     const int BN = N >= 128 ? 128 : N;
     const int kc = x3 == 1 ? 16 : TC_KC;
     const CUtensorMapSwizzle sw = x3 == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
-    const CUtensorMapSwizzle swb = x3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+    const CUtensorMapSwizzle swb = x3 == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
     const CUtensorMapDataType dtb = x3 == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     int splits = gemm_tc_splits(M, N, K, kc);
     const int chunks = K / kc;
@@ -990,9 +1081,9 @@ static int linear_tc_impl(const float *x, const float *w_nk, const float *bias, 
         if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return SIS3D_EINVAL;
-        cuuint64_t dimsb[2] = {(cuuint64_t)K, (cuuint64_t)N * (x3 ? 2 : 1)};
-        cuuint64_t stridesb[1] = {(cuuint64_t)K * (x3 == 2 ? 2 : 4)};
-        cuuint32_t boxb[2] = {(cuuint32_t)kc, (cuuint32_t)BN};
+        cuuint64_t dimsb[2] = {(cuuint64_t)K * (x3 == 2 ? 2 : 1), (cuuint64_t)N * (x3 == 1 ? 2 : 1)};
+        cuuint64_t stridesb[1] = {dimsb[0] * (x3 == 2 ? 2 : 4)};
+        cuuint32_t boxb[2] = {(cuuint32_t)(x3 == 2 ? 64 : kc), (cuuint32_t)BN};
         if (enc(&tmB, dtb, 2, (void *)w_nk, dimsb, stridesb, boxb, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 swb, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return SIS3D_EINVAL;
@@ -1090,7 +1181,8 @@ extern "C" int sis3d_conv3d_tc_f16(const uint16_t *in16, const uint16_t *w16, co
     if (n_tiles <= 0) return SIS3D_OK;
     cudaStream_t s = (cudaStream_t)stream;
     if (wide) {
-        if (ks == 3 && by == 4) return launch_tc<64, 3, 2, 128, 4>(tmA, tmB, a, n_tiles, s);
+        if (ks == 3 && by == 4) return use_cluster() ? launch_tc<64, 3, 2, 128, 4, 0, 0, 2>(tmA, tmB, a, n_tiles, s)
+                                                     : launch_tc<64, 3, 2, 128, 4>(tmA, tmB, a, n_tiles, s);
         if (ks == 3) {
             switch (BN) {
                 case 32: return launch_tc<32, 3, 2, 128>(tmA, tmB, a, n_tiles, s);

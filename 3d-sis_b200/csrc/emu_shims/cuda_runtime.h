@@ -20,6 +20,7 @@ inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline void __trap() { std::abort(); }
 // atomics: relaxed RMW on plain objects, visible to ThreadSanitizer as atomic accesses

@@ -83,9 +83,16 @@ __global__ void __launch_bounds__(256) nms_reduce_kernel(const unsigned long lon
         if (threadIdx.x < rows) s_diag[threadIdx.x] = mask[(size_t)(rb * 64 + threadIdx.x) * cb_total + rb];
         __syncthreads();
         if (threadIdx.x == 0) {
-            unsigned long long cur = s_remv[rb], kept = 0;
-            for (int i = 0; i < rows; ++i)
-                if (!((cur >> i) & 1ULL)) { kept |= 1ULL << i; cur |= s_diag[i]; }
+            // greedy chain over the 64 boxes of this block, visiting only the SURVIVORS (next clear bit of the suppression word):
+            // a single thread's dependent chain, so its length matters -- ~60 kept boxes instead of 400 iterations
+            const unsigned long long rmask = rows >= 64 ? ~0ULL : ((1ULL << rows) - 1ULL);
+            unsigned long long cur = s_remv[rb], kept = 0, avail = ~cur & rmask;
+            while (avail) {
+                const int i = __ffsll((long long)avail) - 1;
+                kept |= 1ULL << i;
+                cur |= s_diag[i];
+                avail = ~cur & rmask & ~((2ULL << i) - 1ULL);  // clear bits above i (i == 63: 2 << 63 == 0 -> nothing left)
+            }
             s_kept = kept;
         }
         __syncthreads();
@@ -299,13 +306,13 @@ __global__ void rpn_pad_kernel(float *rois, float *scores, int32_t *level_ids, c
 }
 
 
-// ---- RPN stages 3-6 in ONE single-CTA kernel: exact top-K, decode + clip, NMS bitmask, greedy reduce, padded outputs ----
-// (the four-kernel chain above costs ~85 us of pure latency per scene: global round trips between single-CTA kernels and an
-// 8-round radix select; here the candidates are sorted directly in shared memory -- the coarse histogram cut of stage 2
-// leaves a few hundred to a few thousand of them -- and the K x K/64 suppression bitmask never leaves shared memory.)
-// Same keys, same decode arithmetic, same IoU bits and the same greedy order as the separate kernels: identical outputs.
-constexpr int kFusedCandCap = 4096;  // candidates sorted in shared memory; more (a huge tie at the cut) -> multi-kernel path
-constexpr int kFusedMaxK = 512;      // pre-NMS top-N the fused kernel handles (TEST uses 400)
+// ---- RPN stage 3 (single CTA): exact top-K by sorting the candidates in shared memory, decode + clip -------------------
+// The coarse histogram cut of stage 2 leaves K plus the population of one 1/2048-wide score bin -- a few hundred to a few
+// thousand keys -- so they are bitonic-sorted directly (no 8-pass radix select, which cost ~16 us of serial latency); only
+// when more than kSortCap candidates share the cut bin is the exact K-th key radix-selected over the global list first.
+// Same keys (score bits | ~flat index: unique, stable descending order) and the same decode arithmetic as
+// rpn_topk_decode_kernel: identical outputs.
+constexpr int kSortCap = 4096;  // candidates sorted in shared memory (32 KB)
 
 __device__ __forceinline__ void decode_box(const RpnLevels &L, int f, float *box, int &lvl_id) {
     int lvl, vox, a, x, y, z;
@@ -330,26 +337,19 @@ __device__ __forceinline__ void decode_box(const RpnLevels &L, int f, float *box
     }
 }
 
-__global__ void __launch_bounds__(1024) rpn_select_nms_kernel(const RpnLevels L, const unsigned long long *cand, const int *cand_count,
-                                                              int K, int cb, float thresh, int post_top_n, float *rois, float *scores,
-                                                              int32_t *level_ids, int32_t *num_out, int32_t *order_out) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(s_raw);           // [kFusedCandCap]
-    unsigned long long *s_mask = s_keys + kFusedCandCap;                                    // [K][cb]
-    unsigned long long *s_remv = s_mask + (size_t)K * cb;                                   // [cb]
-    float *s_box = reinterpret_cast<float *>(s_remv + cb);                                  // [K][6]
-    float *s_score = s_box + (size_t)K * 6;                                                 // [K]
-    int32_t *s_lvl = reinterpret_cast<int32_t *>(s_score + K);                              // [K]
-    __shared__ unsigned long long s_kept, s_prefix;
-    __shared__ int s_nkept, s_hist[256], s_need, s_fill;
+__global__ void __launch_bounds__(1024) rpn_sort_decode_kernel(const RpnLevels L, const unsigned long long *cand, const int *cand_count,
+                                                               int K, float *sorted_boxes, float *sorted_scores,
+                                                               int32_t *sorted_levels, int32_t *order_out, int *n_sorted) {
+    __shared__ unsigned long long s_keys[kSortCap];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_hist[256], s_need, s_fill;
     const int t = threadIdx.x, nt = blockDim.x;
     const int Mtot = *cand_count;
     int M = Mtot;
     const int Keff = min(K, Mtot);
-    for (int j = t; j < cb; j += nt) s_remv[j] = 0;
-    if (t == 0) { s_nkept = 0; s_prefix = 0; s_need = Keff; s_fill = 0; }
+    if (t == 0) { s_prefix = 0; s_need = Keff; s_fill = 0; }
     __syncthreads();
-    if (Mtot > kFusedCandCap) {
+    if (Mtot > kSortCap) {
         // thousands of scores share the histogram bin of the K-th best: radix-select the exact K-th key over the global list
         // first (8 passes), then only the K keys at or above it enter shared memory
         for (int r = 0; r < 8; ++r) {
@@ -373,18 +373,18 @@ __global__ void __launch_bounds__(1024) rpn_select_nms_kernel(const RpnLevels L,
         const unsigned long long T = s_prefix;
         for (int i = t; i < Mtot; i += nt) {
             const unsigned long long k = cand[i];
-            if (k >= T) { const int p = atomicAdd(&s_fill, 1); if (p < kFusedCandCap) s_keys[p] = k; }
+            if (k >= T) { const int p = atomicAdd(&s_fill, 1); if (p < kSortCap) s_keys[p] = k; }
         }
         __syncthreads();
-        M = min(s_fill, kFusedCandCap);  // == K (keys are unique)
+        M = min(s_fill, kSortCap);  // == K (keys are unique)
     }
     int P = 2;
     while (P < M) P <<= 1;  // sort size: every candidate, padded with zero keys (zero sorts last; real keys are non-zero)
     for (int i = t; i < P; i += nt)
-        if (Mtot <= kFusedCandCap) s_keys[i] = i < M ? cand[i] : 0ULL;
+        if (Mtot <= kSortCap) s_keys[i] = i < M ? cand[i] : 0ULL;
         else if (i >= M) s_keys[i] = 0ULL;
     __syncthreads();
-    for (int size = 2; size <= P; size <<= 1)  // bitonic sort, descending (keys are unique: score bits | ~flat index)
+    for (int size = 2; size <= P; size <<= 1)  // bitonic sort, descending
         for (int strd = size >> 1; strd > 0; strd >>= 1) {
             for (int i = t; i < P; i += nt) {
                 const int j = i ^ strd;
@@ -396,8 +396,8 @@ __global__ void __launch_bounds__(1024) rpn_select_nms_kernel(const RpnLevels L,
             }
             __syncthreads();
         }
-    // decode + clip the K best (rows >= Keff: zero boxes that are never emitted)
-    for (int i = t; i < K; i += nt) {
+    if (t == 0) *n_sorted = Keff;
+    for (int i = t; i < K; i += nt) {  // decode + clip the K best (rows >= Keff: zero boxes that are never emitted)
         float box[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         float score = 0.f;
         int lvl_id = 0, f = -1;
@@ -408,33 +408,42 @@ __global__ void __launch_bounds__(1024) rpn_select_nms_kernel(const RpnLevels L,
             decode_box(L, f, box, lvl_id);
         }
 #pragma unroll
-        for (int k = 0; k < 6; ++k) s_box[i * 6 + k] = box[k];
-        s_score[i] = score;
-        s_lvl[i] = lvl_id;
+        for (int k = 0; k < 6; ++k) sorted_boxes[i * 6 + k] = box[k];
+        sorted_scores[i] = score;
+        sorted_levels[i] = lvl_id;
         if (order_out) order_out[i] = f;
     }
-    __syncthreads();
-    // suppression bitmask, upper triangle: word (i, c) bit j <=> IoU(box i, box 64c + j) > thresh for 64c + j > i
-    for (int wd = t; wd < Keff * cb; wd += nt) {
-        const int i = wd / cb, c = wd - i * cb;
-        unsigned long long bits = 0;
-        if (c >= (i >> 6)) {
-            const float *a = s_box + i * 6;
-            const float Sa = box_volume_p1(a);
-            const int jn = min(Keff - c * 64, 64);
-            for (int j = (c == (i >> 6)) ? (i & 63) + 1 : 0; j < jn; ++j)
-                if (iou3d_ref(a, Sa, s_box + (c * 64 + j) * 6) > thresh) bits |= 1ULL << j;
-        }
-        s_mask[wd] = bits;
+}
+
+// ---- NMS greedy reduce with the bitmask staged in shared memory (one coalesced pass over the 22 KB the reduce needs, instead
+// of a global round trip per 64-box block), gather of the first post_top_n survivors and zero padding of the tail ----------
+__global__ void __launch_bounds__(256) nms_reduce_smem_kernel(const unsigned long long *mask, int n_rows, const int *n_limit,
+                                                              int cb_total, NmsGather g, int32_t *num_out) {
+    extern __shared__ unsigned long long s_m[];  // [n_rows][cb_total] then remv[cb_total]
+    unsigned long long *s_remv = s_m + (size_t)n_rows * cb_total;
+    __shared__ unsigned long long s_kept;
+    __shared__ int s_nkept;
+    const int n = n_limit ? min(n_rows, *n_limit) : n_rows;  // rows >= n are padding and never emitted
+    const int t = threadIdx.x, nt = blockDim.x;
+    for (int w = t; w < n * cb_total; w += nt) {
+        const int i = w / cb_total, c = w - i * cb_total;
+        s_m[w] = c >= (i >> 6) ? mask[w] : 0ULL;  // only the upper triangle was written by nms_mask_kernel
     }
+    for (int j = t; j < cb_total; j += nt) s_remv[j] = 0;
+    if (t == 0) s_nkept = 0;
     __syncthreads();
-    // greedy reduce (nms_reduce_kernel's order): in-block chain resolved serially, suppression ORed into later column blocks
-    for (int rb = 0; rb * 64 < Keff; ++rb) {
-        const int rows = min(Keff - rb * 64, 64);
+    for (int rb = 0; rb * 64 < n; ++rb) {
+        const int rows = min(n - rb * 64, 64);
         if (t == 0) {
-            unsigned long long cur = s_remv[rb], kept = 0;
-            for (int i = 0; i < rows; ++i)
-                if (!((cur >> i) & 1ULL)) { kept |= 1ULL << i; cur |= s_mask[(size_t)(rb * 64 + i) * cb + rb]; }
+            // greedy chain visiting only the survivors (see nms_reduce_kernel)
+            const unsigned long long rmask = rows >= 64 ? ~0ULL : ((1ULL << rows) - 1ULL);
+            unsigned long long cur = s_remv[rb], kept = 0, avail = ~cur & rmask;
+            while (avail) {
+                const int i = __ffsll((long long)avail) - 1;
+                kept |= 1ULL << i;
+                cur |= s_m[(size_t)(rb * 64 + i) * cb_total + rb];
+                avail = ~cur & rmask & ~((2ULL << i) - 1ULL);
+            }
             s_kept = kept;
         }
         __syncthreads();
@@ -442,18 +451,18 @@ __global__ void __launch_bounds__(1024) rpn_select_nms_kernel(const RpnLevels L,
         if (t < rows && ((kept >> t) & 1ULL)) {
             const int pos = s_nkept + __popcll(kept & ((1ULL << t) - 1ULL));
             const int i = rb * 64 + t;
-            if (pos < post_top_n) {
+            if (pos < g.post_top_n) {
 #pragma unroll
-                for (int k = 0; k < 6; ++k) rois[pos * 6 + k] = s_box[i * 6 + k];
-                scores[pos] = s_score[i];
-                level_ids[pos] = s_lvl[i];
+                for (int k = 0; k < 6; ++k) g.rois[pos * 6 + k] = g.sorted_boxes[i * 6 + k];
+                g.scores[pos] = g.sorted_scores[i];
+                g.level_ids[pos] = g.sorted_levels[i];
             }
         }
-        const int ncols = cb - rb - 1;
+        const int ncols = cb_total - rb - 1;
         for (int w = t; w < ncols * 64; w += nt) {
             const int i = w & 63, j = rb + 1 + (w >> 6);
             if (i < rows && ((kept >> i) & 1ULL)) {
-                const unsigned long long m = s_mask[(size_t)(rb * 64 + i) * cb + j];
+                const unsigned long long m = s_m[(size_t)(rb * 64 + i) * cb_total + j];
                 if (m) atomicOr(&s_remv[j], m);
             }
         }
@@ -461,18 +470,14 @@ __global__ void __launch_bounds__(1024) rpn_select_nms_kernel(const RpnLevels L,
         if (t == 0) s_nkept += __popcll(kept);
         __syncthreads();
     }
-    const int n = min(s_nkept, post_top_n);
-    if (t == 0) *num_out = n;
-    for (int i = n + t; i < post_top_n; i += nt) {  // zero the padded tail (downstream kernels always process post_top_n rows)
+    const int nk = min(s_nkept, g.post_top_n);
+    if (t == 0) *num_out = nk;
+    for (int i = nk + t; i < g.post_top_n; i += nt) {  // zero the padded tail (downstream kernels always process post_top_n rows)
 #pragma unroll
-        for (int k = 0; k < 6; ++k) rois[i * 6 + k] = 0.f;
-        scores[i] = 0.f;
-        level_ids[i] = 0;
+        for (int k = 0; k < 6; ++k) g.rois[i * 6 + k] = 0.f;
+        g.scores[i] = 0.f;
+        g.level_ids[i] = 0;
     }
-}
-
-static inline size_t fused_smem_bytes(int K, int cb) {
-    return sizeof(unsigned long long) * ((size_t)kFusedCandCap + (size_t)K * cb + cb) + sizeof(float) * 7 * (size_t)K + sizeof(int32_t) * K + 64;
 }
 
 static inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
@@ -557,19 +562,22 @@ extern "C" int sis3d_rpn_proposals(const sis3d_rpn_level *lv, int n_levels, int 
     rpn_score_kernel<<<blocks, 256, 0, s>>>(L, w.keys, w.hist);
     rpn_candidates_kernel<<<blocks, 256, 0, s>>>(w.keys, total, w.hist, pre_top_n, w.cand, w.cand_count);
     const int cb = cdiv(pre_top_n, 64);
-    if (pre_top_n <= kFusedMaxK && !getenv("SIS3D_RPN_UNFUSED")) {
-        // stages 3-6 in one kernel (sorts the candidates in shared memory; if thousands of scores share the histogram bin of
-        // the K-th best it first radix-selects the exact K-th key over the global list, so the result is exact in every case)
+    const size_t reduce_smem = sizeof(unsigned long long) * ((size_t)pre_top_n * cb + cb);
+    if (reduce_smem <= 200 * 1024 && !getenv("SIS3D_RPN_UNFUSED")) {
+        // low-latency chain: sort + decode in one CTA (candidates sorted in shared memory), the K x K/64 IoU bitmask on
+        // cb x cb CTAs (the parallel part), greedy reduce + gather + padding in one CTA with the bitmask staged in shared memory
         static bool attr = false;
-        const size_t smem = fused_smem_bytes(pre_top_n, cb);
         if (!attr) {
-            if (cudaFuncSetAttribute(rpn_select_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_bytes(kFusedMaxK, cdiv(kFusedMaxK, 64))) != cudaSuccess)
+            if (cudaFuncSetAttribute(nms_reduce_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
                 return SIS3D_ELAUNCH;
             attr = true;
         }
-        rpn_select_nms_kernel<<<1, 1024, smem, s>>>(L, w.cand, w.cand_count, pre_top_n, cb, nms_thresh, post_top_n, rois, scores,
-                                                     level_ids, num_out, debug_order);
-        return finish_launch(3);
+        rpn_sort_decode_kernel<<<1, 1024, 0, s>>>(L, w.cand, w.cand_count, pre_top_n, w.sorted_boxes, w.sorted_scores, w.sorted_levels,
+                                                debug_order, w.n_sorted);
+        nms_mask_kernel<<<dim3(cb, cb), 64, 0, s>>>(w.sorted_boxes, pre_top_n, nms_thresh, w.mask, cb);
+        NmsGather g = {w.sorted_boxes, w.sorted_scores, w.sorted_levels, rois, scores, level_ids, post_top_n};
+        nms_reduce_smem_kernel<<<1, 256, reduce_smem, s>>>(w.mask, pre_top_n, w.n_sorted, cb, g, num_out);
+        return finish_launch(5);
     }
     const int Kp2 = next_pow2(pre_top_n);
     if ((size_t)Kp2 * 8 > 48 * 1024)

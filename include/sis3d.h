@@ -211,7 +211,9 @@ int sis3d_linear_tc_x3(const float *x, const float *w_x3, const float *bias, flo
 /* The same compensation with an fp16 operand split ("h3"): v = hi + lo / 2048, hi = fp16(v), lo = fp16((v - hi) * 2048) -- the
  * same 11 + 11 significand bits as the TF32 split -- so the three products are tcgen05 kind::f16 MMAs (2.5x the TF32 rate
  * measured on B200) over 32-channel stages.  Activations stay fp32 in HBM (split in shared memory after the TMA load, |v|
- * clamped to the fp16 range); weights from sis3d_pack_conv_weight_tc_h3 (fp16 [2][cout][ks^3*cin]).  Same arguments as _x3. */
+ * range-limited to fp16: |v| < 65504); weights from sis3d_pack_conv_weight_tc_h3: fp16 [cout][ks^3*cin/32][64], each 128-byte
+ * row = the 32 hi halves of a 32-channel K slice followed by its 32 lo halves (2*cout*ks^3*cin halves in total), so one TMA
+ * row request carries both parts.  Same arguments as _x3. */
 int sis3d_pack_conv_weight_tc_h3(const float *w_oidhw, int cout, int cin, int ks, uint16_t *w_h3, void *stream);
 int sis3d_conv3d_k3_tc_h3(const float *in, const uint16_t *w_h3, const float *bias, const float *residual,
                           int res_ld, int res_coff, float *out, int out_ld, int out_coff, int X, int Y,
