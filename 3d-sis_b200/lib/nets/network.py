@@ -695,6 +695,11 @@ class Network(nn.Module):
 
         todo = [(lvl, f, cfg["NUM_ANCHORS_LEVEL%d" % lvl]) for lvl, f in enumerate(feats, 1)
                 if f is not None and cfg["NUM_ANCHORS_LEVEL%d" % lvl]]
+        if [t[0] for t in todo] != list(range(1, len(todo) + 1)):
+            # the proposal kernel numbers the levels it is given 1..n and RoI pooling reads level k's features for id k; a gap
+            # (e.g. NUM_ANCHORS_LEVEL1 = 0 with level 2 active; the reference keeps the true pyramid level,
+            # proposal_layer.py:150-157) would pool from the wrong map.  No released config has one: refuse instead of guessing.
+            raise S.Sis3dError("active RPN levels must be contiguous from level 1 (NUM_ANCHORS_LEVELn = 0 only for trailing levels)")
         main = torch.cuda.current_stream()
         outs = self._parallel([(lambda t=t: head(*t)) for t in todo])
         levels = []
@@ -1109,11 +1114,23 @@ class Network(nn.Module):
         The yielded dict is only valid until the next iteration."""
         self._check_mode(mode)
         self._ensure_packed()
+        blobs_iter = self._reject_index_lists(blobs_iter)
         self.__dict__["_home_stream"] = torch.cuda.current_stream()  # restored after every slot switch of this loop
         try:
             yield from self._scene_loop(blobs_iter)
         finally:
             self.__dict__["_home_stream"] = None
+
+    @staticmethod
+    def _reject_index_lists(blobs_iter):
+        """The scene loop computes the projection on the device from depth / pose / world2grid; blobs that carry precomputed
+        proj_ind_3d/2d lists need their killing_inds (lib/model/trainval.py:805-822), which this API has no slot for: they go
+        through the synchronous forward(blobs, 'TEST', killing_inds)."""
+        for b in blobs_iter:
+            if "proj_ind_3d" in b:
+                raise S.Sis3dError("forward_pipelined takes depth/pose/world2grid blobs; use forward(blobs, 'TEST', killing_inds) "
+                                   "for blobs with precomputed proj_ind_3d/2d lists")
+            yield b
 
     def _scene_loop(self, blobs_iter):
         from collections import deque

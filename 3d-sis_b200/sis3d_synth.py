@@ -250,8 +250,10 @@ def build_case(port, c):
     return cfg, w, data, views
 
 
-def make_net(c, keep_debug=True, math="fp32", weights=None):
-    """The product Network for a case: released yml config, seeded synthetic weights loaded through load_state_dict."""
+def make_net(c, keep_debug=True, math="fp32", weights=None, enet=False):
+    """The product Network for a case: released yml config, seeded synthetic weights loaded through load_state_dict.
+    enet=True: cfg.USE_IMAGES_GT=False -- the blobs carry RGB frames and the 2-D ENet encoder (seeded default init) is part
+    of the forward."""
     import os
     import torch
     from lib.utils.config import cfg, cfg_from_file, cfg_reset
@@ -259,14 +261,16 @@ def make_net(c, keep_debug=True, math="fp32", weights=None):
     yml = "SUNCG" if c["cfgname"] == "suncg" else "ScanNet"
     cfg_from_file(os.path.join(os.path.dirname(os.path.abspath(__file__)), "experiments", "cfgs", yml, "rpn_class_mask_5.yml"))
     cfg.NUM_CLASSES = 26 if c["cfgname"] == "suncg" else 19
-    cfg.USE_IMAGES, cfg.USE_MASK, cfg.USE_IMAGES_GT = c["use_images"], c["use_mask"], True
+    cfg.USE_IMAGES, cfg.USE_MASK, cfg.USE_IMAGES_GT = c["use_images"], c["use_mask"], not enet
     from lib.nets import backbones
+    import torch as _t
+    _t.manual_seed(1234)  # default-initialised tensors (the ENet encoder when enet=True) are the same in every process
     net = getattr(backbones, cfg.NET)()
     net.init_modules()
     w = weights if weights is not None else make_weights(
         seed=0, net=cfg.NET, use_images=c["use_images"], num_classes=cfg.NUM_CLASSES, a1=cfg.NUM_ANCHORS_LEVEL1,
         a2=cfg.NUM_ANCHORS_LEVEL2, use_mask=c["use_mask"])
-    net.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=not enet)
     net._keep_debug = keep_debug
     net.set_conv_math(math)
     return net, cfg

@@ -296,6 +296,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="sis3d")
     ap.add_argument("--config", default="cfg2")
+    ap.add_argument("--enet", action="store_true",
+                    help="inputs are RGB frames [n,3,256,328]: the 2-D ENet encoder (SURVEY row f2) runs inside the timed region")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lean", action="store_true", help="profiling runs: timed loops only (no latency / parity / CPU legs)")
@@ -322,13 +324,15 @@ def main():
     from lib.model.scene_shard import gather_detections, shard_scenes
     math = os.environ.get("SIS3D_CONV_MATH", wl["math_default"])
     s0 = wl["scenes"][0]
-    st = dict(net=synth.make_net(case_of(wl, s0[1], s0[2]), keep_debug=False, math=math)[0])
+    st = dict(net=synth.make_net(case_of(wl, s0[1], s0[2]), keep_debug=False, math=math, enet=args.enet)[0])
 
     # distinct scenes rotate so that the inputs of consecutive scenes exceed the 126 MB L2: host (pinned) and device copies
     host_in, dev_in = [], []
     for seed, dims, n_img in wl["scenes"]:
         data, boxes = synth.make_scene(seed, dims)
         views = synth.make_views(seed, dims, n_img, boxes)
+        if args.enet:  # normalised RGB frames instead of ENet-shaped features (lib/datasets/dataset.py:255-266)
+            views["feats"] = np.random.default_rng(seed + 7).standard_normal((n_img, 3, 256, 328)).astype(np.float32)
         hb = synth.make_blobs(None, data, views, pin=True)
         host_in.append(hb)
         dev_in.append({"data": hb["data"].to(dev), "id": hb["id"],
@@ -529,11 +533,12 @@ def main():
              "fp16": "f16 operands (convs on tcgen05, fp32 accumulate) + f32"}.get(math, "f32")
     have_traffic = bool(traffic) and args.config == "cfg2" and traffic.get("forward_dram_bytes_per_scene")
     out = {
-        "metric": wl["metric"], "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": wl["metric"] + ("_with_enet" if args.enet else ""), "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
         "dtype": dtype, "data": "synthetic",
-        "config": {"workload": wl["what"], "conv_math": math,
-                   "inputs": "seeded synthetic TSDF + ENet-shaped features/depth/poses; seeded synthetic weights",
+        "config": {"workload": wl["what"] + (" + 2-D ENet encoder on raw RGB frames (row f2)" if args.enet else ""), "conv_math": math,
+                   "inputs": ("seeded synthetic TSDF + RGB frames [n,3,256,328]/depth/poses; seeded synthetic weights" if args.enet else
+                              "seeded synthetic TSDF + ENet-shaped features/depth/poses; seeded synthetic weights"),
                    "l2": f"{len(set(order))} distinct scenes per rank rotate: {l2_bytes / 1e6:.0f} MB of inputs > 126 MB L2 (no flush kernel)",
                    "api": "Network.forward_pipelined (the scene loop; 6 scenes in flight on 6 streams: inputs uploaded one "
                           "scene ahead, 3 static stages overlapping)",
@@ -580,7 +585,7 @@ def main():
         exact = n = 0
         fields, flips = {}, []
         for (dims, n_img), bl in by_shape.items():
-            mk = lambda mode, d=dims, v=n_img: synth.make_net(case_of(wl, d, v), keep_debug=False, math=mode)[0]  # noqa: E731
+            mk = lambda mode, d=dims, v=n_img: synth.make_net(case_of(wl, d, v), keep_debug=False, math=mode, enet=args.enet)[0]  # noqa: E731
             r, _ = parity_rate(mk, bl, math)
             exact += r["exact_scenes"]
             n += r["scenes"]
@@ -600,7 +605,7 @@ def main():
             if m == math:
                 continue
             nn_ = min(B, 48 if m == "fp32" else 192)
-            st["net"], st["order"] = synth.make_net(case_of(wl, s0[1], s0[2]), keep_debug=False, math=m)[0], keep_order[:nn_]
+            st["net"], st["order"] = synth.make_net(case_of(wl, s0[1], s0[2]), keep_debug=False, math=m, enet=args.enet)[0], keep_order[:nn_]
             try:
                 timed_loop(dev_in, 1)
                 ms_o = timed_loop(dev_in, 2)[0]

@@ -41,7 +41,7 @@ def main():
     per_scene = [sum(d["bytes"] for d in seq[a + 1:b + 1] if "sis3d::" in d["name"]) for a, b in zip(half[:-1], half[1:])]
     us_scene = [sum(d["us"] for d in seq[a + 1:b + 1] if "sis3d::" in d["name"]) for a, b in zip(half[:-1], half[1:])]
     n_launch = [sum(1 for d in seq[a + 1:b + 1] if "sis3d::" in d["name"]) for a, b in zip(half[:-1], half[1:])]
-    rpn = [d["bytes"] for d in seq[half[0]:] if re.search(r"conv3d_k3_tc_kernel<128, 3, 4, \d+, 2, 0, [12]>", d["name"])]
+    rpn = [d["bytes"] for d in seq[half[0]:] if re.search(r"conv3d_k3_tc_kernel<128, 3, 4, \d+, 2, 0, [12](, \d+)?>", d["name"])]
     import bench
     out = {"sources_sha": bench.sources_sha(), "capture": os.path.basename(path), "scenes_averaged": len(per_scene),
            "forward_dram_bytes_per_scene": sum(per_scene) / len(per_scene),
