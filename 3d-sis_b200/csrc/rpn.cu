@@ -458,13 +458,20 @@ __global__ void __launch_bounds__(256) nms_reduce_smem_kernel(const unsigned lon
                 g.level_ids[pos] = g.sorted_levels[i];
             }
         }
-        const int ncols = cb_total - rb - 1;
-        for (int w = t; w < ncols * 64; w += nt) {
-            const int i = w & 63, j = rb + 1 + (w >> 6);
-            if (i < rows && ((kept >> i) & 1ULL)) {
-                const unsigned long long m = s_m[(size_t)(rb * 64 + i) * cb_total + j];
-                if (m) atomicOr(&s_remv[j], m);
+        // suppression words of the kept rows -> later column blocks: one WARP per column block ORs its 64 rows with a shuffle
+        // tree and writes the word once (64 threads hammering one shared atomic per block serialised: ~2k cycles per pass)
+        const int ncols = cb_total - rb - 1, lane = t & 31;
+        for (int jj = t >> 5; jj < ncols; jj += nt >> 5) {
+            const int j = rb + 1 + jj;
+            unsigned long long m = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = lane + 32 * h;
+                if (i < rows && ((kept >> i) & 1ULL)) m |= s_m[(size_t)(rb * 64 + i) * cb_total + j];
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+            if (lane == 0 && m) s_remv[j] |= m;
         }
         __syncthreads();
         if (t == 0) s_nkept += __popcll(kept);

@@ -355,7 +355,7 @@ def main():
     l2_bytes = sum(in_bytes(host_in[k]) for k in sorted(set(st["order"])))
 
     def timed_loop(inputs, steps):
-        """`steps` passes of the scene loop (Network.forward_pipelined, 6 scenes in flight) over this rank's scenes; every
+        """`steps` passes of the scene loop (Network.forward_pipelined, 7 scenes in flight) over this rank's scenes; every
         scene's detections and thresholded predicted-class masks are read back to the host.  CUDA events on the default
         stream bracket the region (it waits for the slot streams), barrier + synchronize on both sides, max over ranks."""
         net, order = st["net"], st["order"]
@@ -540,8 +540,8 @@ def main():
                    "inputs": ("seeded synthetic TSDF + RGB frames [n,3,256,328]/depth/poses; seeded synthetic weights" if args.enet else
                               "seeded synthetic TSDF + ENet-shaped features/depth/poses; seeded synthetic weights"),
                    "l2": f"{len(set(order))} distinct scenes per rank rotate: {l2_bytes / 1e6:.0f} MB of inputs > 126 MB L2 (no flush kernel)",
-                   "api": "Network.forward_pipelined (the scene loop; 6 scenes in flight on 6 streams: inputs uploaded one "
-                          "scene ahead, 3 static stages overlapping)",
+                   "api": "Network.forward_pipelined (the scene loop; 7 scenes in flight on 7 streams: inputs uploaded one "
+                          "scene ahead, 4 static stages overlapping)",
                    "scenes_per_step_per_rank": B, "step": f"one pass of the scene loop over {B} scenes per rank",
                    "rois_per_scene": nroi, "mask_rois_per_scene": nmask, "mask_voxels_per_scene": vox,
                    "scenes_per_rank": n_scenes, "timed_seconds": ms_dev / 1e3,
@@ -635,7 +635,17 @@ def main():
                              "algorithmic_tflops": 0.894e6 * mvox / (mh * 1e-3) / 1e12,
                              "what": "ragged mask stage alone (plan + 6 layers + select) on 10 RoIs of 54x22x22, teacher-forced table"}
     if not (args.no_cpu_baseline or args.lean) and world == 1:
-        out["cpu_baseline"], _ = cpu_arm(wl, args.cpu_baseline_seconds)
+        # the reference's package is called `lib` like ours, so its CPU arm runs in a process of its own (the same code path as
+        # `--impl reference`); only if that fails is the in-process oracle port timed instead (kind "port")
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", args.config,
+                                "--steps", "6", "--warmup", "1"], capture_output=True, text=True, timeout=400,
+                               env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+            out["cpu_baseline"] = json.loads(line)["cpu_baseline"]
+        except Exception as e:
+            print(f"[bench] reference subprocess failed ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+            out["cpu_baseline"], _ = cpu_arm(wl, args.cpu_baseline_seconds)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
