@@ -20,11 +20,22 @@
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16, THREADS = 256, TM = 4, TN = 4, AS_LD = BM + 4, KTAB = 512;
+constexpr int BK = 16, THREADS = 256, TN = 4, KTAB = 512;
 
+// N tile BN_ in {16, 32, 64} (ENet's bottleneck convs produce 16 / 32 channels: a fixed 64-wide tile wasted 50-75 % of the FMAs);
+// 256 threads = (BN_/4) x (1024/BN_) register tiles of TM x 4, so the M tile is BM_ = TM * 1024 / BN_ rows (TM = 4: 256 / 128 /
+// 64 rows; TM = 2 halves it for the launches whose grid would otherwise leave most SMs idle: 5 views of 32 x 41 pixels are
+// only 6560 rows).
+// VEC: NHWC input with C_in % 4 == 0 (every layer but the first): four consecutive k = four channels of one tap = ONE float4 load
+// instead of four scalar gathers with their index arithmetic.  Per output the products are still accumulated k = 0 .. K-1 in
+// order with fmaf, so every variant produces the same bits.
+template <int BN_, bool VEC, int TM = 4>
 __global__ void __launch_bounds__(THREADS) enet_conv2d_kernel(const sis3d_enet_conv a) {
+    constexpr int NTX = BN_ / TN, NTY = THREADS / NTX, BM_ = NTY * TM, AS_LD = BM_ + 4;
+    static_assert(BM_ % 64 == 0, "the A loader fills 64 rows per pass");
+    constexpr int ROWS_PER_T = BM_ / 64;  // A loader: 64 rows x 4 k-quads per pass
     __shared__ __align__(16) float As[BK][AS_LD];
-    __shared__ __align__(16) float Bs[BK][BN];
+    __shared__ __align__(16) float Bs[BK][BN_];
     __shared__ int s_ktab[KTAB];  // k -> ky | kx << 4 | c << 8
 
     const int t = threadIdx.x;
@@ -37,55 +48,89 @@ __global__ void __launch_bounds__(THREADS) enet_conv2d_kernel(const sis3d_enet_c
     __syncthreads();
 
     const int64_t m_total = (int64_t)a.N * a.Ho * a.Wo;
-    const int64_t m_base = (int64_t)blockIdx.x * BM;
-    const int n0 = blockIdx.y * BN;
+    const int64_t m_base = (int64_t)blockIdx.x * BM_;
+    const int n0 = blockIdx.y * BN_;
 
-    // A loader: row lr of the tile, 4 consecutive k at lq*4
+    // A loader: rows lr + 64 p (p < ROWS_PER_T) of the tile, 4 consecutive k at lq*4
     const int lr = t >> 2, lq = t & 3;
-    const int64_t lm = m_base + lr;
-    const bool lvalid = lm < m_total;
-    int ln = 0, loy = 0, lox = 0;
-    if (lvalid) {
-        ln = (int)(lm / ((int64_t)a.Ho * a.Wo));
-        const int rem = (int)(lm - (int64_t)ln * a.Ho * a.Wo);
-        loy = rem / a.Wo;
-        lox = rem - loy * a.Wo;
+    bool lvalid[ROWS_PER_T];
+    int by[ROWS_PER_T], bx[ROWS_PER_T];
+    const float *in_base[ROWS_PER_T];
+#pragma unroll
+    for (int p = 0; p < ROWS_PER_T; ++p) {
+        const int64_t lm = m_base + lr + 64 * p;
+        lvalid[p] = lm < m_total;
+        int ln = 0, loy = 0, lox = 0;
+        if (lvalid[p]) {
+            ln = (int)(lm / ((int64_t)a.Ho * a.Wo));
+            const int rem = (int)(lm - (int64_t)ln * a.Ho * a.Wo);
+            loy = rem / a.Wo;
+            lox = rem - loy * a.Wo;
+        }
+        by[p] = loy * a.stride - a.pad_y;
+        bx[p] = lox * a.stride - a.pad_x;
+        in_base[p] = a.in + (int64_t)ln * a.in_sn;
     }
-    const int by = loy * a.stride - a.pad_y, bx = lox * a.stride - a.pad_x;
-    const float *in_base = a.in + (int64_t)ln * a.in_sn;
     // B loader: row bk, 4 consecutive columns at bc
-    const int bk = t / (BN / 4), bc = (t % (BN / 4)) * 4;
-    const bool b_thread = t < BK * (BN / 4);
+    const int bk = t / (BN_ / 4), bc = (t % (BN_ / 4)) * 4;
+    const bool b_thread = t < BK * (BN_ / 4);
 
-    const int tx = t % (BN / TN), ty = t / (BN / TN);
+    const int tx = t % NTX, ty = t / NTX;
     float acc[TM][TN];
 #pragma unroll
     for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-    auto fetch = [&](int k0, float4 &av, float4 &bv) {
-        float tmp[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int k = k0 + lq * 4 + i;
-            if (lvalid && k < K) {
-                int ky, kx, c;
-                if (k < KTAB) {
-                    const int e = s_ktab[k];
+    auto fetch = [&](int k0, float4 *av, float4 &bv) {
+        const int kq = k0 + lq * 4;
+        if constexpr (VEC) {
+            int ky = 0, kx = 0, c = 0;
+            const bool kin = kq < K;  // K % 4 == 0: the quad is either entirely inside or entirely outside
+            if (kin) {
+                if (kq < KTAB) {
+                    const int e = s_ktab[kq];
                     ky = e & 15; kx = (e >> 4) & 15; c = e >> 8;
                 } else {
-                    const int tap = k / a.cin;
-                    c = k - tap * a.cin;
+                    const int tap = kq / a.cin;
+                    c = kq - tap * a.cin;
                     ky = tap / a.kw;
                     kx = tap - ky * a.kw;
                 }
-                const int iy = by + ky * a.dil, ix = bx + kx * a.dil;
-                if ((unsigned)iy < (unsigned)a.H && (unsigned)ix < (unsigned)a.W)
-                    tmp[i] = __ldg(in_base + (int64_t)iy * a.in_sy + (int64_t)ix * a.in_sx + (int64_t)c * a.in_sc);
+            }
+#pragma unroll
+            for (int p = 0; p < ROWS_PER_T; ++p) {
+                av[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int iy = by[p] + ky * a.dil, ix = bx[p] + kx * a.dil;
+                if (kin && lvalid[p] && (unsigned)iy < (unsigned)a.H && (unsigned)ix < (unsigned)a.W)
+                    av[p] = __ldg(reinterpret_cast<const float4 *>(in_base[p] + (int64_t)iy * a.in_sy + (int64_t)ix * a.in_sx + c));
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < ROWS_PER_T; ++p) {
+                float tmp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = kq + i;
+                    if (lvalid[p] && k < K) {
+                        int ky, kx, c;
+                        if (k < KTAB) {
+                            const int e = s_ktab[k];
+                            ky = e & 15; kx = (e >> 4) & 15; c = e >> 8;
+                        } else {
+                            const int tap = k / a.cin;
+                            c = k - tap * a.cin;
+                            ky = tap / a.kw;
+                            kx = tap - ky * a.kw;
+                        }
+                        const int iy = by[p] + ky * a.dil, ix = bx[p] + kx * a.dil;
+                        if ((unsigned)iy < (unsigned)a.H && (unsigned)ix < (unsigned)a.W)
+                            tmp[i] = __ldg(in_base[p] + (int64_t)iy * a.in_sy + (int64_t)ix * a.in_sx + (int64_t)c * a.in_sc);
+                    }
+                }
+                av[p] = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
             }
         }
-        av = make_float4(tmp[0], tmp[1], tmp[2], tmp[3]);
         bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (b_thread) {
             const int k = k0 + bk, n = n0 + bc;
@@ -93,21 +138,30 @@ __global__ void __launch_bounds__(THREADS) enet_conv2d_kernel(const sis3d_enet_c
         }
     };
 
-    float4 av, bv;
+    float4 av[ROWS_PER_T], bv;
     if (K > 0) fetch(0, av, bv);
     for (int k0 = 0; k0 < K; k0 += BK) {
         __syncthreads();
-        As[lq * 4 + 0][lr] = av.x;
-        As[lq * 4 + 1][lr] = av.y;
-        As[lq * 4 + 2][lr] = av.z;
-        As[lq * 4 + 3][lr] = av.w;
+#pragma unroll
+        for (int p = 0; p < ROWS_PER_T; ++p) {
+            As[lq * 4 + 0][lr + 64 * p] = av[p].x;
+            As[lq * 4 + 1][lr + 64 * p] = av[p].y;
+            As[lq * 4 + 2][lr + 64 * p] = av[p].z;
+            As[lq * 4 + 3][lr + 64 * p] = av[p].w;
+        }
         if (b_thread) *reinterpret_cast<float4 *>(&Bs[bk][bc]) = bv;
         __syncthreads();
         if (k0 + BK < K) fetch(k0 + BK, av, bv);
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
-            const float4 v = *reinterpret_cast<const float4 *>(&As[k][ty * TM]);
-            const float ar[TM] = {v.x, v.y, v.z, v.w};
+            float ar[TM];
+            if constexpr (TM == 4) {
+                const float4 v = *reinterpret_cast<const float4 *>(&As[k][ty * TM]);
+                ar[0] = v.x; ar[1] = v.y; ar[2] = v.z; ar[3] = v.w;
+            } else {
+                const float2 v = *reinterpret_cast<const float2 *>(&As[k][ty * TM]);
+                ar[0] = v.x; ar[1] = v.y;
+            }
             const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tx * TN]);
 #pragma unroll
             for (int i = 0; i < TM; ++i) {
@@ -228,8 +282,25 @@ extern "C" int sis3d_enet_conv2d(const sis3d_enet_conv *p, void *stream) {
     if (a.res && (a.res_c <= 0 || a.res_c > a.cout || a.res_ld < a.res_c)) return -1;
     if (((uintptr_t)a.w) & 15) return -1;
     const int64_t m_total = (int64_t)a.N * a.Ho * a.Wo;
-    dim3 grid((unsigned)((m_total + BM - 1) / BM), (unsigned)((a.cout + BN - 1) / BN));
-    SIS3D_LAUNCH(enet_conv2d_kernel, grid, dim3(THREADS), stream, a);
+    // narrowest N tile that covers cout (16 / 32 / 64 per grid column), vectorised gather for NHWC inputs with C_in % 4 == 0
+    const bool vec = a.in_sc == 1 && a.cin % 4 == 0 && ((uintptr_t)a.in & 15) == 0 && a.in_sx % 4 == 0 && a.in_sy % 4 == 0 && a.in_sn % 4 == 0;
+    const int bn = a.cout <= 16 ? 16 : (a.cout <= 32 ? 32 : 64);
+    const int ntiles = (a.cout + bn - 1) / bn;
+    // TM = 2 (half-height M tiles) when the 4-row tiling would launch fewer than two CTAs per SM and the narrow N tile allows it
+    const bool half = bn < 64 && ((m_total + 4096 / bn - 1) / (4096 / bn)) * ntiles < 2 * 148;
+    const int bm = (half ? 2048 : 4096) / bn;
+    dim3 grid((unsigned)((m_total + bm - 1) / bm), (unsigned)ntiles);
+#define SIS3D_ENET_GO(BNV, VECV, TMV) SIS3D_LAUNCH((enet_conv2d_kernel<BNV, VECV, TMV>), grid, dim3(THREADS), stream, a)
+    if (bn == 16) {
+        if (vec) { if (half) SIS3D_ENET_GO(16, true, 2); else SIS3D_ENET_GO(16, true, 4); }
+        else { if (half) SIS3D_ENET_GO(16, false, 2); else SIS3D_ENET_GO(16, false, 4); }
+    } else if (bn == 32) {
+        if (vec) { if (half) SIS3D_ENET_GO(32, true, 2); else SIS3D_ENET_GO(32, true, 4); }
+        else { if (half) SIS3D_ENET_GO(32, false, 2); else SIS3D_ENET_GO(32, false, 4); }
+    } else {
+        if (vec) SIS3D_ENET_GO(64, true, 4); else SIS3D_ENET_GO(64, false, 4);
+    }
+#undef SIS3D_ENET_GO
     return done();
 }
 
