@@ -71,7 +71,7 @@ SYMBOLS = ["sis3d_strerror", "sis3d_version", "sis3d_launch_count", "sis3d_nms_w
            "sis3d_rpn_workspace_bytes", "sis3d_rpn_proposals", "sis3d_detect_decode", "sis3d_mask_plan_build", "sis3d_mask_stage_launch", "sis3d_memcpy_async",
            "sis3d_mask_select", "sis3d_pack_conv_weight_tc_x3", "sis3d_conv3d_k3_tc_x3", "sis3d_conv3d_k3_tc_fused_x3",
            "sis3d_linear_tc_x3", "sis3d_pack_conv_weight_tc_h3", "sis3d_conv3d_k3_tc_h3", "sis3d_conv3d_k3_tc_fused_h3",
-           "sis3d_linear_tc_h3"]
+           "sis3d_linear_tc_h3", "sis3d_chunk_decode"]
 # include/sis3d_enet.h
 SYMBOLS_ENET = ["sis3d_enet_pack_weight", "sis3d_enet_conv2d", "sis3d_enet_pool_affine", "sis3d_enet_to_nchw"]
 

@@ -36,7 +36,12 @@ def part_in_chunk(b):
 
 
 class Dataset(torch.utils.data.Dataset):
-    def __init__(self, data_location, mode="test", view_provider=None, label_mapping=None, label_weights=None):
+    def __init__(self, data_location, mode="test", view_provider=None, label_mapping=None, label_weights=None,
+                 device_decode=False):
+        """device_decode=True: the voxel block is NOT transposed / TSDF-encoded on the host (four full-volume numpy passes,
+        ~3 ms per chunk -- more than the whole GPU forward); the item carries the raw float32 block as stored in the file
+        ('sdf_raw', pinned) and `collate_fn` turns it into the network input on the device with sis3d_chunk_decode."""
+        self.device_decode = bool(device_decode)
         if isinstance(data_location, (list, tuple)):
             self.scenes = list(data_location)
         elif os.path.isdir(data_location):
@@ -57,8 +62,8 @@ class Dataset(torch.utils.data.Dataset):
 
     def __getitem__(self, idx):
         path = self.scenes[idx]
-        s = read_scene(path)
-        data = encode_tsdf(s["sdf"], float(cfg.TRUNCATED))
+        s = read_scene(path, raw_sdf=self.device_decode)
+        data = None if self.device_decode else encode_tsdf(s["sdf"], float(cfg.TRUNCATED))
         gt_box = s["boxes"].copy()
         gt_box[:, 0:3] = np.floor(gt_box[:, 0:3])
         gt_box[:, 3:6] = np.ceil(gt_box[:, 3:6])
@@ -82,21 +87,49 @@ class Dataset(torch.utils.data.Dataset):
         keep = [i for i, b in enumerate(gt_box) if b[1] <= max_h and b[4] <= max_h]
         gt_box = gt_box[keep] if len(keep) else np.zeros((0, 7), np.float32)
         masks = [masks[i] for i in keep if i < len(masks)]
-        data = data[:, :, :max_h, :]
-        item = {"id": path, "data": np.ascontiguousarray(data), "gt_box": gt_box, "gt_mask": masks,
-                "nearest_images": {}, "image_files": []}
+        if self.device_decode:
+            X, Y, Z = s["dims"]
+            vol_dims = (X, min(Y, max_h), Z)
+            item = {"id": path, "sdf_raw": torch.from_numpy(np.array(s["sdf"], dtype=np.float32)), "sdf_dims": (X, Y, Z),
+                    "y_keep": max_h, "gt_box": gt_box, "gt_mask": masks, "nearest_images": {}, "image_files": []}
+            if torch.cuda.is_available():
+                item["sdf_raw"] = item["sdf_raw"].pin_memory()
+        else:
+            data = data[:, :, :max_h, :]
+            vol_dims = data.shape[1:]
+            item = {"id": path, "data": np.ascontiguousarray(data), "gt_box": gt_box, "gt_mask": masks,
+                    "nearest_images": {}, "image_files": []}
         if cfg.USE_IMAGES:
             if self.view_provider is None:
                 raise RuntimeError("USE_IMAGES=True needs a view_provider (depth/pose/features source)")
-            item["nearest_images"] = self.view_provider(path, s["frame_ids"], s["world2grid"], data.shape[1:])
+            item["nearest_images"] = self.view_provider(path, s["frame_ids"], s["world2grid"], vol_dims)
         return item
+
+
+def decode_on_device(sdf_raw, dims, y_keep, device=None):
+    """Raw x-fastest float32 block of a .scene/.chunk file -> network input [1,2,X,Y',Z] on the device (sis3d_chunk_decode)."""
+    import ctypes as C
+    from lib import _sis3d as S
+    X, Y, Z = (int(v) for v in dims)
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    raw = sdf_raw.to(dev, non_blocking=True)
+    Yk = min(Y, int(y_keep))
+    data = torch.empty(1, 2, X, Yk, Z, dtype=torch.float32, device=dev)
+    S.check(S.lib.sis3d_chunk_decode(S.ptr(raw), X, Y, Z, int(y_keep), C.c_float(float(cfg.TRUNCATED)), S.ptr(data), S.stream()),
+            "chunk_decode")
+    raw.record_stream(torch.cuda.current_stream())
+    return data
 
 
 def collate_fn(batch):
     """batch size 1 collate matching the blobs layout Network.forward expects (dataloader.py:8-44)."""
     assert len(batch) == 1, "the inference path processes one scene at a time"
     b = batch[0]
-    blobs = {"id": [b["id"]], "data": torch.from_numpy(b["data"]).unsqueeze(0), "gt_box": [torch.from_numpy(b["gt_box"])],
+    if "sdf_raw" in b:  # device decode: raw block H2D + one kernel on the current stream (csrc/io.cu)
+        data = decode_on_device(b["sdf_raw"], b["sdf_dims"], b["y_keep"])
+    else:
+        data = torch.from_numpy(b["data"]).unsqueeze(0)
+    blobs = {"id": [b["id"]], "data": data, "gt_box": [torch.from_numpy(b["gt_box"])],
              "gt_mask": [b["gt_mask"]], "image_files": b["image_files"]}
     if b["nearest_images"]:
         v = b["nearest_images"]

@@ -32,19 +32,22 @@ class _Cursor:
         return self.pos >= len(self.buf)
 
 
-def read_scene(path):
+def read_scene(path, raw_sdf=False):
     """-> dict(sdf[X,Y,Z] f32, boxes[n,7] (min xyz, max xyz, raw label), masks [list of (label, u16[X,Y,Z])],
-    part_in_volume[n] | None, world2grid[4,4] | None, frame_ids[n_img] | None)."""
+    part_in_volume[n] | None, world2grid[4,4] | None, frame_ids[n_img] | None).
+    raw_sdf=True: `sdf` is left as stored in the file -- a flat float32 array, x fastest -- and `dims` = (X, Y, Z) is added: the
+    layout sis3d_chunk_decode consumes on the device (no host-side transposition or TSDF encoding)."""
     with open(path, "rb") as f:
         cur = _Cursor(f.read())
     X, Y, Z = (int(v) for v in cur.take("<u8", 3))
-    sdf = cur.take("<f4", X * Y * Z).reshape((X, Y, Z), order="F").astype(np.float32)
+    flat = cur.take("<f4", X * Y * Z)
+    sdf = flat if raw_sdf else flat.reshape((X, Y, Z), order="F").astype(np.float32)
     n_box = int(cur.take("<u4")[0])
     boxes = np.zeros((n_box, 7), dtype=np.float32)
     for i in range(n_box):
         boxes[i, :6] = cur.take("<f4", 6)
         boxes[i, 6] = cur.take("<u4")[0]
-    out = dict(sdf=sdf, boxes=boxes, masks=[], part_in_volume=None, world2grid=None, frame_ids=None)
+    out = dict(sdf=sdf, dims=(X, Y, Z), boxes=boxes, masks=[], part_in_volume=None, world2grid=None, frame_ids=None)
     if cur.eof:
         return out
     n_mask = int(cur.take("<u4")[0])

@@ -25,25 +25,29 @@ def scene_key(scene_id):
     return os.path.basename(str(scene_id))[:12]
 
 
-def detections_from_predictions(net):
+def detections_from_predictions(net_or_predictions):
     """-> pred_class int64[n], pred_conf float64[n], pred_box float32[n,6], keep bool[n] (trainval.py:825-858)."""
-    det = net._predictions["detections_host"]
+    P = getattr(net_or_predictions, "_predictions", net_or_predictions)
+    det = P["detections_host"]
     return det[:, 7].astype(np.int64), det[:, 6].astype(np.float64), det[:, 0:6].astype(np.float32), det[:, 8] > 0.5
 
 
-def save_scene_results(out_dir, scene_id, blobs, net):
+def save_scene_results(out_dir, scene_id, blobs, net_or_predictions):
+    """Result files of one scene from `net._predictions` (synchronous forward) or the dict the scene loop yields."""
+    P = getattr(net_or_predictions, "_predictions", net_or_predictions)
     d = os.path.join(out_dir, scene_key(scene_id))
     os.makedirs(d, exist_ok=True)
-    pred_class, pred_conf, pred_box, keep = detections_from_predictions(net)
+    pred_class, pred_conf, pred_box, keep = detections_from_predictions(P)
     np.save(os.path.join(d, "pred_class"), pred_class)
     np.save(os.path.join(d, "pred_conf"), pred_conf)
     np.save(os.path.join(d, "pred_box"), pred_box)
-    np.save(os.path.join(d, "scene"), np.where(blobs["data"][0, 0].numpy() <= 1, 1, 0))
+    np.save(os.path.join(d, "scene"), np.where(blobs["data"][0, 0].cpu().numpy() <= 1, 1, 0))
     if cfg.USE_MASK:
         masks = []
-        if keep.any():  # one D2H of the thresholded predicted-class channels (csrc/roi.cu mask_select_kernel)
-            bits = net._predictions["mask_bits"].cpu().numpy()
-            offs, sizes = net._predictions["mask_offsets"], net._predictions["mask_sizes"]
+        if keep.any():  # the thresholded predicted-class channels (csrc/roi.cu mask_select_kernel): already on the host when the
+            # scene loop produced them, else one D2H
+            bits = P["mask_bits_host"] if "mask_bits_host" in P else P["mask_bits"].cpu().numpy()
+            offs, sizes = P["mask_offsets"], P["mask_sizes"]
             for j in range(len(sizes)):
                 masks.append(bits[int(offs[j]):int(offs[j + 1])].reshape(tuple(int(v) for v in sizes[j])).astype(np.float32))
         with open(os.path.join(d, "pred_mask"), "wb") as f:
@@ -53,13 +57,32 @@ def save_scene_results(out_dir, scene_id, blobs, net):
     return d
 
 
-def run_scenes(net, data_loader, out_dir, skip_existing=False):
+def run_scenes(net, data_loader, out_dir, skip_existing=False, pipelined=True):
+    """The scene loop of SolverWrapper.test / .benchmark (trainval.py:787-911).  pipelined=True drives it through
+    Network.forward_pipelined (several scenes in flight, results read back asynchronously); blobs that carry precomputed
+    projection index lists (the reference's calling convention) go through the synchronous forward."""
     os.makedirs(out_dir, exist_ok=True)
     t0 = time.time()
     done = 0
-    for blobs in data_loader:
-        if skip_existing and os.path.isdir(os.path.join(out_dir, scene_key(blobs["id"][0]))):  # trainval.py:647-653
-            continue
+
+    def todo():
+        for blobs in data_loader:
+            if skip_existing and os.path.isdir(os.path.join(out_dir, scene_key(blobs["id"][0]))):  # trainval.py:647-653
+                continue
+            yield blobs
+    it = todo()
+    if pipelined:
+        first = next(it, None)
+        if first is not None and "proj_ind_3d" not in first:
+            import itertools
+            for blobs, P in net.forward_pipelined(itertools.chain([first], it)):
+                save_scene_results(out_dir, blobs["id"][0], blobs, P)
+                done += 1
+            it = iter(())
+        elif first is not None:
+            import itertools
+            it = itertools.chain([first], it)
+    for blobs in it:
         net.forward(blobs, "TEST", None)
         save_scene_results(out_dir, blobs["id"][0], blobs, net)
         done += 1
@@ -71,9 +94,14 @@ def run_scenes(net, data_loader, out_dir, skip_existing=False):
 def _build(args, mode, view_provider=None):
     from lib.nets import backbones
     filelist = cfg.TEST_FILELIST
-    dataset = Dataset(filelist, mode, view_provider=view_provider)
-    loader = torch.utils.data.DataLoader(dataset, batch_size=1, shuffle=False, num_workers=getattr(args, "num_workers", 0),
-                                         collate_fn=collate_fn)
+    workers = getattr(args, "num_workers", 0)
+    dataset = Dataset(filelist, mode, view_provider=view_provider, device_decode=(workers == 0))
+    if workers == 0:
+        # files are read + parsed a few scenes ahead in a background thread; the voxel block is decoded on the device
+        from lib.datasets.prefetch import Prefetcher
+        loader = (collate_fn([item]) for item in Prefetcher((dataset[i] for i in range(len(dataset))), depth=6))
+    else:
+        loader = torch.utils.data.DataLoader(dataset, batch_size=1, shuffle=False, num_workers=workers, collate_fn=collate_fn)
     net = getattr(backbones, cfg.NET)()
     net.init_modules()
     ckpt = os.path.join(args.output_dir, "step_{}.pth".format(args.step))

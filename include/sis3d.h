@@ -189,6 +189,14 @@ int sis3d_conv3d_k3_tc_fused(const float *in, const float *w2_tc, const float *b
                              int Y, int Z, int cin, int cmid, int cout, int act, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Voxel block of a `.scene` / `.chunk` file -> network input, on the device (replaces the host numpy passes of
+ * lib/datasets/dataset.py:50-68 + the height crop :192-205).  sdf_xfast: the raw float32 block as stored in the file
+ * (index = x + X*(y + Y*z)); data: [2][X][min(Y, y_keep)][Z] (z fastest): channel 0 = |clip(sdf, -truncation, truncation)|,
+ * channel 1 = (sdf > -1) as 0/1.  Exact (no rounding involved).
+ * ---------------------------------------------------------------------------------------------- */
+int sis3d_chunk_decode(const float *sdf_xfast, int X, int Y, int Z, int y_keep, float truncation, float *data, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Error-compensated 3xTF32 on the tensor cores ("x3"): same call sites and arguments as sis3d_conv3d_k3_tc /
  * _fused / sis3d_linear_tc, fp32-class accuracy.  Every fp32 operand is split v = hi + lo (hi = tf32(v), round to
  * nearest; lo = tf32(v - hi)) and the product accumulated as A_lo.B_hi + A_hi.B_lo + A_hi.B_hi in the fp32 TMEM

@@ -40,7 +40,7 @@ def emu_lib(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("emu") / "libsis3d_emu.so")
     # SIS3D_EMU_TSAN=1 + LD_PRELOAD=libtsan.so turns the emulated tests into a shared-memory racecheck (profiles/)
     cuda_host_emu.build(out, [os.path.join(ROOT, "3d-sis_b200", "csrc", f)
-                              for f in ("conv_simt.cu", "rpn.cu", "roi.cu", "sparse.cu", "project.cu")],
+                              for f in ("conv_simt.cu", "rpn.cu", "roi.cu", "sparse.cu", "project.cu", "io.cu")],
                         tsan=os.environ.get("SIS3D_EMU_TSAN") == "1")
     lib = C.CDLL(out)
     for f in ("sis3d_nms_workspace_bytes", "sis3d_rpn_workspace_bytes", "sis3d_project_compact_workspace_bytes",
