@@ -359,9 +359,11 @@ def main():
         scene's detections and thresholded predicted-class masks are read back to the host.  CUDA events on the default
         stream bracket the region (it waits for the slot streams), barrier + synchronize on both sides, max over ranks."""
         net, order = st["net"], st["order"]
+        # rank-0-only sections (after the other ranks have left: parity, other math modes) must not touch a collective
+        multi = world > 1 and not st.get("solo", False)
         d2h = 0
         k0 = net.kernel_launches()
-        if world > 1:
+        if multi:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -376,7 +378,7 @@ def main():
                 if mine is not None:
                     t = torch.from_numpy(det)
                     local_det.append((mine[j], t[:, :6], t[:, 7], t[:, 6]))
-            if mine is not None and world > 1:  # cfg4: every rank ends a pass with all scenes' detections (NCCL all_gather)
+            if mine is not None and multi:  # cfg4: every rank ends a pass with all scenes' detections (NCCL all_gather)
                 allres = gather_detections(local_det, device=dev)
                 assert len(allres) == len(wl["scene_list"])
         for sl in net._slots:
@@ -384,10 +386,10 @@ def main():
                 torch.cuda.current_stream().wait_stream(sl["stream"])
         e1.record()
         torch.cuda.synchronize()
-        if world > 1:
+        if multi:
             dist.barrier()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
+        if multi:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         vox = nroi = nmask = 0
         for det in dets:  # workload statistics, outside the timed region
@@ -415,7 +417,7 @@ def main():
     wsteps = max(1, min(args.warmup, max(1, 64 // B)))
     timed_loop(dev_in, wsteps)   # warm-up passes; also capture the graphs of the pipeline slots
     timed_loop(host_in, wsteps)
-    if args.host_profile and rank == 0:
+    if args.host_profile and rank == 0 and world == 1:  # (a rank-0-only pass would wait at the barrier forever)
         import cProfile
         import io
         import pstats
@@ -462,6 +464,7 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
+    st["solo"] = True  # from here on rank 0 works alone: no collective may be issued (the other ranks are gone)
     lat_dev = latency(dev_in, 30) if not args.lean else None
     lat_host = latency(host_in, 30) if not args.lean else None
 
