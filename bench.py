@@ -465,8 +465,10 @@ def main():
             dist.destroy_process_group()
         return
     st["solo"] = True  # from here on rank 0 works alone: no collective may be issued (the other ranks are gone)
-    lat_dev = latency(dev_in, 30) if not args.lean else None
-    lat_host = latency(host_in, 30) if not args.lean else None
+    # single-GPU properties (latency, parity rate, other math modes, mask-heavy point, CPU arm) are reported by the N = 1 line only
+    extras = not args.lean and world == 1
+    lat_dev = latency(dev_in, 30) if extras else None
+    lat_host = latency(host_in, 30) if extras else None
 
     # dominant tensor-core kernel, timed live through the C ABI: rpn_net_level{1,2} = 3x3x3 conv 128 -> 256 on the 24x12x24
     # level grid (12.231 GFLOP algorithmic), 40 back-to-back launches between two CUDA events on the launching stream
@@ -578,7 +580,7 @@ def main():
                   "tf32_tflops_burst_measured_here": tf32_peak, "source": pk["source"]},
         "clocks": clock_summary,
     }
-    if not args.lean:
+    if extras:
         # ---- parity of THIS math mode on THESE inputs: fraction of scenes whose integer outputs equal the fp32 CUDA-core path
         from lib.utils.parity import parity_rate
         uniq = sorted(set(order))[:24]
@@ -637,7 +639,7 @@ def main():
         out["mask_heavy"] = {"rois": 10, "crop": [54, 22, 22], "mask_voxels": mvox, "ms": mh,
                              "algorithmic_tflops": 0.894e6 * mvox / (mh * 1e-3) / 1e12,
                              "what": "ragged mask stage alone (plan + 6 layers + select) on 10 RoIs of 54x22x22, teacher-forced table"}
-    if not (args.no_cpu_baseline or args.lean) and world == 1:
+    if extras and not args.no_cpu_baseline:
         # the reference's package is called `lib` like ours, so its CPU arm runs in a process of its own (the same code path as
         # `--impl reference`); only if that fails is the in-process oracle port timed instead (kind "port")
         try:
