@@ -5,12 +5,13 @@ for p in (os.path.join(ROOT, "3d-sis_b200"), ROOT, os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import numpy as np, torch
 torch.set_num_threads(1)
-import bench
+import sis3d_synth as _synth
 from sis3d_synth import make_net
 from sis3d_synth import CASES
 dev = torch.device("cuda", 0)
-net, cfg = make_net(CASES["cfg2_96x48x96"], keep_debug=False, math=os.environ.get("SIS3D_CONV_MATH", "mixed"))
-data, views = bench.case(1000)
+net, cfg = make_net(CASES["cfg2_96x48x96"], keep_debug=False, math=os.environ.get("SIS3D_CONV_MATH", "exact"))
+data, _boxes = _synth.make_scene(1000, (96, 48, 96))
+views = _synth.make_views(1000, (96, 48, 96), 5, _boxes)
 blobs = {"data": torch.from_numpy(data).to(dev), "id": ["x"],
          "nearest_images": {"images": [torch.from_numpy(views["feats"]).to(dev)], "depths": [torch.from_numpy(views["depths"]).to(dev)],
                             "poses": [torch.from_numpy(views["poses"])], "world2grid": [torch.from_numpy(views["world2grid"])]}}

@@ -7,13 +7,14 @@ import numpy as np, torch
 if os.environ.get("SIS3D_HOST_THREADS"):
     torch.set_num_threads(int(os.environ["SIS3D_HOST_THREADS"]))
 print("torch threads", torch.get_num_threads(), "cpu_count", os.cpu_count(), "affinity", len(os.sched_getaffinity(0)))
-import bench
+import sis3d_synth as _synth
 from sis3d_synth import make_net
 from sis3d_synth import CASES
 
 dev = torch.device("cuda", 0)
-net, cfg = make_net(CASES["cfg2_96x48x96"], keep_debug=False, math=os.environ.get("SIS3D_CONV_MATH", "mixed"))
-data, views = bench.case(1000)
+net, cfg = make_net(CASES["cfg2_96x48x96"], keep_debug=False, math=os.environ.get("SIS3D_CONV_MATH", "exact"))
+data, _boxes = _synth.make_scene(1000, (96, 48, 96))
+views = _synth.make_views(1000, (96, 48, 96), 5, _boxes)
 blobs = {"data": torch.from_numpy(data).to(dev), "id": ["x"],
          "nearest_images": {"images": [torch.from_numpy(views["feats"]).to(dev)], "depths": [torch.from_numpy(views["depths"]).to(dev)],
                             "poses": [torch.from_numpy(views["poses"])], "world2grid": [torch.from_numpy(views["world2grid"])]}}
