@@ -29,7 +29,13 @@ def sub(t, step=7):
                                        float(a.max()), float(a.min())])
 
 
-def run_forward(tag, yml, dims, n_img, seed, use_images, use_mask, net_name):
+def digest(a):
+    """sha1 of an index array's bytes (whole-scene cases: 40 views of up to 83 k indices would be 20 MB as arrays)."""
+    import hashlib
+    return np.frombuffer(hashlib.sha1(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8).copy()
+
+
+def run_forward(tag, yml, dims, n_img, seed, use_images, use_mask, net_name, compact=False):
     cfg = rh.load_cfg(yml, USE_IMAGES=use_images, USE_IMAGES_GT=True, USE_MASK=use_mask)
     from lib.layer_utils.projection import ProjectionHelper
     num_classes = cfg.NUM_CLASSES
@@ -55,8 +61,11 @@ def run_forward(tag, yml, dims, n_img, seed, use_images, use_mask, net_name):
         for i, m in enumerate(maps):
             if m is not None:
                 k = int(m[0][0])
-                g[f"proj3d_{i}"] = m[0][1:1 + k].numpy().astype(np.int32)
-                g[f"proj2d_{i}"] = m[1][1:1 + k].numpy().astype(np.int16)
+                p3, p2 = m[0][1:1 + k].numpy().astype(np.int32), m[1][1:1 + k].numpy().astype(np.int16)
+                if compact:
+                    g[f"proj_count_{i}"], g[f"proj3d_sha_{i}"], g[f"proj2d_sha_{i}"] = np.array(k), digest(p3), digest(p2)
+                else:
+                    g[f"proj3d_{i}"], g[f"proj2d_{i}"] = p3, p2
         g["killing_inds"] = np.array(killing, dtype=np.int64)
         blobs["proj_ind_3d"] = [torch.stack([m[0] for m in real])]
         blobs["proj_ind_2d"] = [torch.stack([m[1] for m in real])]
@@ -64,13 +73,13 @@ def run_forward(tag, yml, dims, n_img, seed, use_images, use_mask, net_name):
     net.forward(blobs, "TEST", killing)
     P = net._predictions
     if use_images:
-        g["imageft_sub"], g["imageft_stats"] = sub(net._imageft, 97)
+        g["imageft_sub"], g["imageft_stats"] = sub(net._imageft, 997 if compact else 97)
     g["rois"] = P["rois"][0].numpy()
     g["roi_scores"] = P["roi_scores"][0].numpy()
     g["level_inds"] = P["level_inds"][0].numpy()
     for lvl in (1, 2):
-        g[f"rpn_prob_sub_l{lvl}"], g[f"rpn_prob_stats_l{lvl}"] = sub(P[f"rpn_cls_prob_level{lvl}"][0, 1], 5)
-        g[f"rpn_bbox_sub_l{lvl}"], g[f"rpn_bbox_stats_l{lvl}"] = sub(P[f"rpn_bbox_pred_level{lvl}"], 11)
+        g[f"rpn_prob_sub_l{lvl}"], g[f"rpn_prob_stats_l{lvl}"] = sub(P[f"rpn_cls_prob_level{lvl}"][0, 1], 53 if compact else 5)
+        g[f"rpn_bbox_sub_l{lvl}"], g[f"rpn_bbox_stats_l{lvl}"] = sub(P[f"rpn_bbox_pred_level{lvl}"], 101 if compact else 11)
     g["cls_prob"] = P["cls_prob"].numpy()
     g["cls_pred"] = P["cls_pred"].numpy()
     g["bbox_pred"] = P["bbox_pred"].numpy()
@@ -91,8 +100,12 @@ def run_forward(tag, yml, dims, n_img, seed, use_images, use_mask, net_name):
         assert keep.sum() == len(masks), (keep.sum(), len(masks))
         for j, i in enumerate(np.nonzero(keep)[0]):
             m = masks[j][0].numpy()  # [num_classes,w,h,l]
-            g[f"mask_{j}_cls"] = m[pc[i]]
-            g[f"mask_{j}_allcls_sub"] = m.reshape(-1)[::13].copy()
+            if compact:  # the predicted class's mask, strided, + the number of voxels above the driver's 0.5 threshold
+                g[f"mask_{j}_cls_sub"] = m[pc[i]].reshape(-1)[::7].copy()
+                g[f"mask_{j}_cls_on"] = np.array(int((m[pc[i]] > 0.5).sum()))
+            else:
+                g[f"mask_{j}_cls"] = m[pc[i]]
+                g[f"mask_{j}_allcls_sub"] = m.reshape(-1)[::13].copy()
     path = os.path.join(OUT, f"forward_{tag}.npz")
     np.savez_compressed(path, **g)
     print(f"[golden] {tag}: rois={len(g['rois'])} masks={int(g.get('mask_keep', np.zeros(0)).sum())} "
@@ -135,7 +148,7 @@ def run_operators():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
-    which = sys.argv[1:] or ["ops", "cfg1", "odd", "cfg2"]
+    which = sys.argv[1:] or ["ops", "cfg1", "odd", "cfg2", "suncg", "scene", "stress"]
     if "ops" in which:
         run_operators()
     if "cfg1" in which:
@@ -146,3 +159,10 @@ if __name__ == "__main__":
         run_forward("cfg2_96x48x96", "ScanNet/rpn_class_mask_5.yml", (96, 48, 96), 5, 303, True, True, "ScanNet_Backbone")
     if "suncg" in which:
         run_forward("suncg_40x24x40", "SUNCG/rpn_class_mask_5.yml", (40, 24, 40), 3, 404, True, True, "SUNCG_Backbone")
+    # whole-scene shapes of BASELINE configs[2] (same seeds as tests/test_gpu_forward.py's whole-scene tests), compact fixtures
+    if "scene" in which:
+        run_forward("scene_88x44x88", "ScanNet/rpn_class_mask_5.yml", (88, 44, 88), 8, 505, True, True, "ScanNet_Backbone",
+                    compact=True)
+    if "stress" in which:
+        run_forward("stress_208x48x160", "ScanNet/rpn_class_mask_5.yml", (208, 48, 160), 40, 606, True, True,
+                    "ScanNet_Backbone", compact=True)

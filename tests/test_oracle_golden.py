@@ -49,6 +49,48 @@ def test_port_matches_reference_forward(oracle, tag):
             np.testing.assert_allclose(m.reshape(-1)[::13], g[f"mask_{j}_allcls_sub"], atol=1e-5)
 
 
+WHOLE_SCENES = {  # BASELINE configs[2] shapes; seeds shared with tests/test_gpu_forward.py's whole-scene tests
+    "scene_88x44x88": dict(cfgname="scannet", dims=(88, 44, 88), n_img=8, seed=505, use_images=True, use_mask=True),
+    "stress_208x48x160": dict(cfgname="scannet", dims=(208, 48, 160), n_img=40, seed=606, use_images=True, use_mask=True),
+}
+
+
+@pytest.mark.parametrize("tag", list(WHOLE_SCENES))
+def test_port_matches_reference_whole_scene(oracle, tag):
+    """The oracle at the fully-convolutional whole-scene shapes (up to 1.6 M voxels, 40 views), against compact fixtures of
+    the unmodified reference (oracle/make_golden.py scene stress): per-view index lists by sha1, strided samples of the
+    dense tensors, the complete RoI / class / box tables and strided masks."""
+    import hashlib
+    c = WHOLE_SCENES[tag]
+    g = load_golden(f"forward_{tag}.npz")
+    cfg, w, data, views = build_case(oracle, c)
+    out = oracle.forward(cfg, w, data, views)
+    assert list(g["killing_inds"]) == out["killing_inds"]
+    sha = lambda a: np.frombuffer(hashlib.sha1(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+    for i in range(c["n_img"]):
+        m = oracle.compute_projection(cfg, views["depths"][i], views["poses"][i], views["world2grid"], c["dims"])
+        assert len(m[0]) == int(g[f"proj_count_{i}"]), f"view {i} count"
+        assert np.array_equal(sha(m[0].astype(np.int32)), g[f"proj3d_sha_{i}"]), f"view {i} lin3d"
+        assert np.array_equal(sha(m[1].astype(np.int16)), g[f"proj2d_sha_{i}"]), f"view {i} lin2d"
+    assert np.array_equal(sub(out["imageft"], 997), g["imageft_sub"])
+    for lvl in (1, 2):
+        np.testing.assert_allclose(sub(out[f"rpn_prob_level{lvl}"], 53), g[f"rpn_prob_sub_l{lvl}"], atol=2e-6)
+        np.testing.assert_allclose(sub(out[f"rpn_deltas_level{lvl}"], 101), g[f"rpn_bbox_sub_l{lvl}"], atol=2e-5)
+    assert out["rois"].shape == g["rois"].shape
+    np.testing.assert_allclose(out["rois"].numpy(), g["rois"], atol=1e-3)
+    np.testing.assert_allclose(out["roi_scores"].numpy().reshape(-1), g["roi_scores"].reshape(-1), atol=2e-6)
+    assert np.array_equal(out["level_inds"].numpy(), g["level_inds"])
+    np.testing.assert_allclose(out["cls_prob"].numpy(), g["cls_prob"], atol=1e-5)
+    assert np.array_equal(out["cls_pred"].numpy(), g["cls_pred"])
+    np.testing.assert_allclose(out["bbox_pred"].numpy(), g["bbox_pred"], atol=1e-5)
+    np.testing.assert_allclose(out["pred_box"], g["pred_box"], atol=1e-3)
+    assert np.array_equal(out["mask_keep"], g["mask_keep"])
+    for j, i in enumerate(np.nonzero(out["mask_keep"])[0]):
+        m = out["mask_pred"][j][0].numpy()[int(g["cls_pred"][i])]
+        np.testing.assert_allclose(m.reshape(-1)[::7], g[f"mask_{j}_cls_sub"], atol=1e-5)
+        assert abs(int((m > 0.5).sum()) - int(g[f"mask_{j}_cls_on"])) <= 1  # a voxel within 1e-5 of the threshold may flip
+
+
 def test_port_operators(oracle):
     g = load_golden("operators.npz")
     for seed in range(6):
