@@ -156,3 +156,70 @@ def test_mlp_tail_emulated_vs_torch(emu):
     h = F.relu(F.linear(F.relu(F.linear(x1, w2, b2)), w3, b3))
     torch.testing.assert_close(cls, F.linear(h, wc, bc), atol=1e-4, rtol=1e-4)
     torch.testing.assert_close(box, F.linear(h, wb, bb), atol=1e-4, rtol=1e-4)
+
+
+# ---------------------------------------------------------------- edge cases of the C entry points (no GPU needed)
+def test_nms_emulated_empty_identical_and_many_blocks(oracle, emu):
+    """n = 0 (the reference's gpu_nms is never called with it; the entry point must still report 0 survivors), every box
+    identical (one survivor), disjoint boxes (all survive) and a list spanning many 64-box bitmask words."""
+    num = torch.full((1,), 77, dtype=torch.int32)
+    keep = torch.empty(1, dtype=torch.int64)
+    ws = torch.empty(max(int(emu.sis3d_nms_workspace_bytes(0)), 8), dtype=torch.uint8)
+    assert emu.sis3d_nms(None, 0, C.c_float(0.1), _p(keep), _p(num), _p(ws), None) == 0
+    assert int(num) == 0
+    for name, boxes, thr in (
+            ("identical", np.tile(np.array([[3, 4, 5, 20, 21, 22]], np.float32), (130, 1)), 0.5),
+            ("disjoint", np.array([[10 * i, 0, 0, 10 * i + 5, 5, 5] for i in range(200)], np.float32), 0.1),
+            ("many words", synth.make_nms_boxes(8, 1500), 0.3)):
+        b = torch.from_numpy(boxes)
+        n = len(boxes)
+        keep = torch.empty(n, dtype=torch.int64)
+        num = torch.zeros(1, dtype=torch.int32)
+        ws = torch.empty(int(emu.sis3d_nms_workspace_bytes(n)), dtype=torch.uint8)
+        assert emu.sis3d_nms(_p(b), n, C.c_float(thr), _p(keep), _p(num), _p(ws), None) == 0, name
+        want = oracle.nms3d(boxes, thr, fma_mode=1)
+        assert np.array_equal(keep[:int(num)].numpy(), want), name
+        if name == "identical":
+            assert int(num) == 1
+        if name == "disjoint":
+            assert int(num) == n
+
+
+def test_roi_pool_emulated_zero_rois_and_degenerate_boxes(oracle, emu):
+    rng = np.random.default_rng(4)
+    Cn, dims = 4, (9, 5, 7)
+    feat = torch.from_numpy(rng.standard_normal((Cn,) + dims).astype(np.float32))
+    out = torch.full((1, Cn, 4, 4, 4), 5.0)
+    none = torch.zeros(1, 6)
+    assert emu.sis3d_roi_pool_fwd(_p(feat), 0, C.c_float(0.25), 0, *dims, Cn, 4, 4, 4, _p(none), _p(out), None, None) == 0
+    assert (out == 5.0).all()  # nothing written for zero RoIs
+    assert emu.sis3d_roi_pool_fwd(_p(feat), 0, C.c_float(0.25), 0, *dims, Cn, 4, 4, 4, None, _p(out), None, None) != 0  # NULL rois: EINVAL
+    # zero-extent box, a box entirely outside the map (empty bins -> 0 / argmax -1), a box hanging over the far border
+    rois = np.array([[8, 8, 8, 8, 8, 8], [100, 100, 100, 120, 110, 115], [30, 15, 22, 60, 40, 50], [-5, -5, -5, 3, 3, 3]], np.float32)
+    want_out, want_arg = oracle.roi_pool3d(feat.numpy()[None], rois, (4, 4, 4), 0.25)
+    r = torch.from_numpy(rois)
+    out = torch.empty(len(rois), Cn, 4, 4, 4)
+    arg = torch.empty(len(rois), Cn, 4, 4, 4, dtype=torch.int32)
+    assert emu.sis3d_roi_pool_fwd(_p(feat), 0, C.c_float(0.25), len(rois), *dims, Cn, 4, 4, 4, _p(r), _p(out), _p(arg), None) == 0
+    assert np.array_equal(out.numpy(), np.asarray(want_out)) and np.array_equal(arg.numpy(), np.asarray(want_arg))
+
+
+def test_rpn_proposals_emulated_scene_smaller_than_every_anchor(oracle, host_S):
+    """No anchor lies inside a 1x1x1-cell level grid of a 4^3 scene with ALLOW_BORDER = 0: zero candidates, zero RoIs, padded rows
+    all zero (lib/layer_utils/proposal_layer.py:36-43 keeps nothing; the reference would then fail in torch.cat -- here the
+    stage reports an empty result)."""
+    from lib.layer_utils.proposal_layer import rpn_proposals
+    from lib.utils.config import cfg_from_file, cfg_reset
+    cfg_reset()
+    cfg_from_file(os.path.join(ROOT, "3d-sis_b200", "experiments", "cfgs", "ScanNet", "rpn_class_mask_5.yml"))
+    dims, scene = (1, 1, 1), (4, 4, 4)
+    rng = np.random.default_rng(0)
+    levels = []
+    for A, tab in ((3, "scannet14_3.txt"), (11, "scannet14_11.txt")):
+        sizes = oracle.read_anchor_table(tab)
+        assert not oracle.inside_mask(oracle.generate_anchors(dims, sizes, 4), scene).any()
+        levels.append(dict(cls=torch.from_numpy(rng.standard_normal((1, 2 * A)).astype(np.float32)),
+                           deltas=torch.from_numpy(rng.standard_normal((1, 6 * A)).astype(np.float32)),
+                           sizes=torch.tensor(sizes, dtype=torch.float32), grid=dims, A=A, cls_mode=0))
+    rois, scores, lvl, num, order = rpn_proposals(levels, scene, "TEST", want_order=True)
+    assert int(num.item()) == 0 and not rois.any() and not lvl.any()
