@@ -77,3 +77,36 @@ def test_backprojection_dense_and_sparse_fused_emulated(oracle, host_S):
                                                  C.c_size_t(nbytes), None))
     ref = F.relu(F.conv3d(want, w, stride=2))[0].permute(1, 2, 3, 0)
     torch.testing.assert_close(out, ref, atol=2e-5, rtol=1e-4)
+
+
+def test_backprojection_emulated_with_dead_views(oracle, host_S):
+    """A view whose depth map is empty contributes nothing and is reported in killing_inds by the reference's driver
+    (lib/model/trainval.py:805-822: compute_projection returns None); with EVERY view dead the volume is all zero."""
+    S = host_S
+    dims, n_img, Cn = (24, 14, 20), 3, 8
+    ocfg = oracle.make_cfg("scannet")
+    v = _views(dims, n_img, 202)
+    intr = ocfg.INTRINSIC
+    for dead in ((1,), (0, 1, 2)):
+        depths = v["depths"].copy()
+        for i in dead:
+            depths[i] = 0.0
+        vp = P._view_params_torch(intr, (41, 32), ocfg.PROJ_DEPTH_MIN, ocfg.PROJ_DEPTH_MAX, dims, torch.from_numpy(v["poses"]),
+                                  torch.from_numpy(v["world2grid"]))
+        pix, counts = P.project_maps(vp, torch.from_numpy(depths).contiguous(), (intr[0][0], intr[1][1], intr[0][2], intr[1][2]),
+                                     (ocfg.PROJ_DEPTH_MIN, ocfg.PROJ_DEPTH_MAX, ocfg.VOXEL_SIZE), dims, 41, 32)
+        got_dead = [i for i in range(n_img) if int(counts[i]) == 0]
+        assert set(dead) <= set(got_dead)  # (a synthetic view may already look away from the volume)
+        feats = torch.from_numpy(v["feats"][:, :Cn]).contiguous()
+        pairs, n_pairs = torch.empty(3 * n_img, dtype=torch.int32), torch.empty(1, dtype=torch.int32)
+        S.check(S.lib.sis3d_backproject_pairs(S.ptr(counts), n_img, S.ptr(pairs), S.ptr(n_pairs), None))
+        vol = P.backproject(feats, pix, pairs, n_pairs, dims, 41, 32)
+        if len(got_dead) == n_img:  # the reference's driver fails here (zip(*[])); this path yields the empty volume
+            import pytest
+            with pytest.raises(ValueError):
+                oracle.backproject_views(ocfg, v["feats"][:, :Cn], depths, v["poses"], v["world2grid"], dims)
+            assert not vol.any()
+        else:
+            want, killed = oracle.backproject_views(ocfg, v["feats"][:, :Cn], depths, v["poses"], v["world2grid"], dims)
+            assert list(killed) == got_dead
+            assert torch.equal(vol.permute(3, 0, 1, 2), want[0])
